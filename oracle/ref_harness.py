@@ -1,0 +1,380 @@
+"""Reference harness -- TEST INFRASTRUCTURE, runs only in the build container.
+
+Executes the UNMODIFIED reference scripts under /root/reference (read-only) on a
+synthetic workload and captures (a) the artefacts the hot path consumes
+(QUANT_WEIGHTS_K.pickle, bias_scales/, max_a.txt -> tests/golden/workload_k{K}.npz)
+and (b) golden outputs of stage_8_torch_full_quant.Yolov8.forward for a set of
+seeded synthetic images (-> tests/golden/golden_k{K}.npz).
+
+Nothing here is imported by the product.  /root/reference does not exist on the
+GPU box, so this file is never run there; its outputs are committed fixtures.
+
+Recipe follows SURVEY.md Appendix C:
+  * package alias  yolov8n_quantisation -> /root/reference   (overlay dir of symlinks,
+    with a generated stage_0.py when K != 8, Appendix C.7)
+  * sys.modules stubs for deeplake / map_boxes / ultralytics / matplotlib / seaborn
+  * cwd with utils/cats_2_640.jpg and {K}_nano/
+  * os.utime re-stamp of weights_pickle/* before stage_7 (Python 3.12 gzip handles)
+  * Tensor.argsort(stable=True) forced while the reference NMS runs (hard part 3)
+
+Usage:  python oracle/ref_harness.py --k 8 [--work /tmp/ayq_work] [--skip-pipeline]
+"""
+import argparse
+import hashlib
+import io
+import os
+import runpy
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from oracle import synth  # noqa: E402  (seeded image / weight generators shared with tests)
+
+# execution order of conv_quant() calls in stage_6_full_quant.py (= SURVEY Appendix B order)
+LAYER_ORDER = [
+    'Conv_P1', 'Conv_P2', 'C2F_2_conv_0', 'C2F_2_bottle_0', 'C2F_2_bottle_1', 'C2F_2_conv_1',
+    'Conv_P3', 'C2F_4_conv_0', 'C2F_4_bottle_0', 'C2F_4_bottle_1', 'C2F_4_bottle_2', 'C2F_4_bottle_3', 'C2F_4_conv_1',
+    'Conv_P4', 'C2F_6_conv_0', 'C2F_6_bottle_0', 'C2F_6_bottle_1', 'C2F_6_bottle_2', 'C2F_6_bottle_3', 'C2F_6_conv_1',
+    'Conv_P5', 'C2F_8_conv_0', 'C2F_8_bottle_0', 'C2F_8_bottle_1', 'C2F_8_conv_1',
+    'SPPF_conv_0', 'SPPF_conv_1',
+    'C2F_12_conv_0', 'C2F_12_bottle_0', 'C2F_12_bottle_1', 'C2F_12_conv_1',
+    'C2F_15_conv_0', 'C2F_15_bottle_0', 'C2F_15_bottle_1', 'C2F_15_conv_1',
+    'Conv_16', 'C2F_18_conv_0', 'C2F_18_bottle_0', 'C2F_18_bottle_1', 'C2F_18_conv_1',
+    'Conv_19', 'C2F_21_conv_0', 'C2F_21_bottle_0', 'C2F_21_bottle_1', 'C2F_21_conv_1',
+    'x_result_5_up_0', 'x_result_5_up_1', 'x_result_5_up_2',
+    'x_result_5_down_0', 'x_result_5_down_1', 'x_result_5_down_2',
+    'x_result_6_up_0', 'x_result_6_up_1', 'x_result_6_up_2',
+    'x_result_6_down_0', 'x_result_6_down_1', 'x_result_6_down_2',
+    'x_up_0', 'x_up_1', 'x_up_2', 'x_down_0', 'x_down_1', 'x_down_2',
+    'dfl',
+]
+
+
+# --------------------------------------------------------------------------- environment
+def make_overlay(work, k):
+    """Package alias; for K != 8 an overlay whose stage_0.py is generated (Appendix C.7)."""
+    pkg_root = os.path.join(work, 'pkg')
+    os.makedirs(pkg_root, exist_ok=True)
+    alias = os.path.join(pkg_root, 'yolov8n_quantisation')
+    if os.path.islink(alias) or os.path.exists(alias):
+        return pkg_root
+    if k == 8:
+        os.symlink(REF, alias)
+        return pkg_root
+    os.makedirs(os.path.join(alias, 'quantisation'))
+    qsrc = os.path.join(REF, 'quantisation')
+    for name in os.listdir(qsrc):
+        if name == 'stage_0.py':
+            continue
+        os.symlink(os.path.join(qsrc, name), os.path.join(alias, 'quantisation', name))
+    with open(os.path.join(qsrc, 'stage_0.py')) as f:
+        src = f.read()
+    assert 'K = 8' in src
+    with open(os.path.join(alias, 'quantisation', 'stage_0.py'), 'w') as f:
+        f.write(src.replace('K = 8', f'K = {k}', 1))
+    return pkg_root
+
+
+def install_stubs(calib_images):
+    for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.patches', 'seaborn'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['matplotlib'].patches = sys.modules['matplotlib.patches']
+
+    mb = types.ModuleType('map_boxes')
+    mb.mean_average_precision_for_boxes = lambda *a, **k: (0.0, {})
+    sys.modules['map_boxes'] = mb
+
+    dl = types.ModuleType('deeplake')
+
+    class _DS:
+        def pytorch(self, num_workers=0, batch_size=1, transform=None, shuffle=False):
+            tf = transform['images']
+            for img_u8 in calib_images:           # HWC uint8 ndarray
+                yield {'images': tf(img_u8).unsqueeze(0),
+                       'boxes': torch.zeros((1, 1, 4)), 'categories': torch.zeros((1, 1))}
+
+        def __repr__(self):
+            return f'<synthetic calibration set, {len(calib_images)} images>'
+
+    dl.load = lambda *a, **k: _DS()
+    sys.modules['deeplake'] = dl
+
+    ul = types.ModuleType('ultralytics')
+
+    class YOLO:
+        """Stands in for the checkpoint: stage_1 maps weights BY POSITION (stage_1.py:771-779),
+        so we hand back stage_1's own freshly-initialised model tensors, re-randomised by
+        oracle.synth.synth_float_weights (BN statistics, dfl=arange(16), class-branch tuning)."""
+
+        def __init__(self, path):
+            frame = sys._getframe(1)
+            m = frame.f_globals['model']
+            self._sd = synth.synth_float_weights(m.state_dict(), m)
+
+        def state_dict(self):
+            return self._sd
+
+    ul.YOLO = YOLO
+    sys.modules['ultralytics'] = ul
+
+
+def run_stage(pkg_root, name):
+    t0 = time.time()
+    path = os.path.join(pkg_root, 'yolov8n_quantisation', 'quantisation', name)
+    out = io.StringIO()
+    real_stdout = sys.stdout
+    sys.stdout = out
+    try:
+        g = runpy.run_path(path, run_name='__main__')
+    finally:
+        sys.stdout = real_stdout
+    print(f'[harness] {name}: {time.time() - t0:.1f}s')
+    return g
+
+
+def run_pipeline(work, pkg_root, k):
+    """stage_1 -> 2 -> 4 -> 5 -> 6_full_quant -> 7, unmodified."""
+    main_dir = f'{k}_nano'
+    run_stage(pkg_root, 'stage_1.py')
+    run_stage(pkg_root, 'stage_2.py')
+    run_stage(pkg_root, 'stage_4.py')
+    run_stage(pkg_root, 'stage_5.py')
+
+    # stage_6_full_quant: silence the Verilog / first-pixel dumps and the sleeps (Appendix C.5);
+    # arithmetic untouched.  `from module import *` copies these names at import time, so patch
+    # the defining modules first.
+    import importlib
+    sw = importlib.import_module('yolov8n_quantisation.quantisation.utils.save_weights')
+    cp = importlib.import_module('yolov8n_quantisation.quantisation.utils.conv2d_print_fp')
+    rt = importlib.import_module('yolov8n_quantisation.quantisation.utils.result_txt')
+    noop = lambda *a, **kw: None
+    for mod in (sw, cp, rt):
+        for nm in dir(mod):
+            if nm.startswith('save_txt') or nm in ('conv2d', 'result_txt', 'add_rescale_shift', 'add_silu'):
+                setattr(mod, nm, noop)
+    real_sleep = time.sleep
+    time.sleep = noop
+    try:
+        run_stage(pkg_root, 'stage_6_full_quant.py')
+    finally:
+        time.sleep = real_sleep
+    import gc
+    gc.collect()  # finalise the unclosed gzip handles (Appendix C.4)
+
+    wp = os.path.join(main_dir, 'weights_pickle')
+    t = time.time() - 10000
+    for i, layer in enumerate(LAYER_ORDER):
+        for j, suffix in enumerate(('conv', 'bias')):
+            p = os.path.join(wp, f'{layer}_{suffix}.pickle')
+            assert os.path.exists(p), p
+            os.utime(p, (t + 2 * i + j, t + 2 * i + j))
+    run_stage(pkg_root, 'stage_7.py')
+
+
+# --------------------------------------------------------------------------- capture
+def sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()[:16]
+
+
+def capture_goldens(work, pkg_root, k, images_u8, keep_full, dump_dir=None):
+    """Import stage_8_torch_full_quant and record every integer tensor of forward()."""
+    g = run_stage(pkg_root, 'stage_8_torch_full_quant.py')
+    model = g['model']
+    fwd_globals = g['silu'].__globals__
+    rec = {}
+    state = {}
+
+    real_silu = g['silu']
+    real_requantize = g['requantize']
+    real_coord_quant = g['coord_quant']
+    real_conv_forward = torch.nn.Conv2d.forward
+
+    def conv_forward(self, x):
+        y = real_conv_forward(self, x)
+        state['n_conv'] += 1
+        # exactness certificate: fp32 conv == fp64 conv, integer inputs
+        if state['certify']:
+            y64 = torch.nn.functional.conv2d(x.double(), self.weight.double(),
+                                             None if self.bias is None else self.bias.double(),
+                                             self.stride, self.padding)
+            state['conv_mismatch'] += int((y64 != y.double()).sum())
+            state['max_abs_in'] = max(state['max_abs_in'], float(x.abs().max()))
+            state['max_abs_acc'] = max(state['max_abs_acc'], float(y.abs().max()))
+            state['non_integer_in'] += int((x != x.round()).sum())
+        state['conv_out'].append(y)
+        return y
+
+    def silu(x, scale_x, a_input):
+        r = real_silu(x, scale_x, a_input)
+        state['silu_out'].append(r[0].clone())
+        return r
+
+    def requantize(arr, old, new, bits, device, bit_size_for_koeff=8):
+        r = real_requantize(arr, old, new, bits, device, bit_size_for_koeff)
+        state['coeffs'].append((np.asarray(r[1], dtype=np.float64).reshape(-1),
+                                np.asarray(r[2], dtype=np.float64).reshape(-1)))
+        if not state['in_silu']:
+            state['requant_out'].append(r[0].clone())
+        return r
+
+    def silu_wrapped(x, scale_x, a_input):
+        state['in_silu'] = True
+        try:
+            return silu(x, scale_x, a_input)
+        finally:
+            state['in_silu'] = False
+
+    def coord_quant(pred):
+        state['dbox_cls'] = pred.clone()
+        real_argsort = torch.Tensor.argsort
+
+        def stable_argsort(self, *a, **kw):
+            kw['stable'] = True
+            return real_argsort(self, *a, **kw)
+        torch.Tensor.argsort = stable_argsort
+        try:
+            return real_coord_quant(pred)
+        finally:
+            torch.Tensor.argsort = real_argsort
+
+    fwd_globals['silu'] = silu_wrapped
+    fwd_globals['requantize'] = requantize
+    fwd_globals['coord_quant'] = coord_quant
+    torch.nn.Conv2d.forward = conv_forward
+
+    out = {}
+    cert = dict(conv_mismatch=0, max_abs_in=0.0, max_abs_acc=0.0, non_integer_in=0)
+    try:
+        for i, img_u8 in enumerate(images_u8):
+            state.update(n_conv=0, conv_out=[], silu_out=[], requant_out=[], in_silu=False, coeffs=[],
+                         dbox_cls=None, certify=(i < 2), conv_mismatch=0, max_abs_in=0.0,
+                         max_abs_acc=0.0, non_integer_in=0)
+            x = synth.to_input_tensor(img_u8)
+            t0 = time.time()
+            with torch.no_grad():
+                boxes, classes = model(x)
+            dt = time.time() - t0
+            assert state['n_conv'] == 64, state['n_conv']          # 63 convs + dfl
+            assert len(state['silu_out']) == 57
+            convs = state['conv_out']
+            # the six raw head accumulators are conv outputs 47,50,53,56,59,62 (0-based, Appendix B order)
+            pre = f'img{i}_'
+            # canonical hash form: NCHW int32 bytes
+            i32 = lambda t: t.numpy().astype(np.int32)
+            out[pre + 'silu_sha'] = np.array([sha(i32(t)) for t in state['silu_out']])
+            out[pre + 'conv_sha'] = np.array([sha(i32(t)) for t in convs[:63]])
+            out[pre + 'requant_sha'] = np.array([sha(i32(t)) for t in state['requant_out']])
+            d = state['dbox_cls'][0].numpy()                        # (84, 8400) fp32, integer valued
+            out[pre + 'dbox_sha'] = np.array(sha(d[:4].astype(np.int32)))
+            out[pre + 'cls_sha'] = np.array(sha(d[4:].astype(np.int32)))
+            out[pre + 'dbox'] = d[:4].astype(np.int32)
+            out[pre + 'score_max'] = d[4:].max(0).astype(np.int32)
+            out[pre + 'score_arg'] = d[4:].argmax(0).astype(np.int16)
+            if boxes is None:
+                out[pre + 'boxes'] = np.zeros((0, 4), np.float32)
+                out[pre + 'classes'] = np.zeros((0, 2), np.float32)
+            else:
+                out[pre + 'boxes'] = boxes.numpy().astype(np.float32)
+                out[pre + 'classes'] = classes.numpy().astype(np.float32)
+            ncand = int((d[4:].max(0) > 8192).sum())
+            out[pre + 'ncand'] = np.array(ncand)
+            if dump_dir and i in keep_full:
+                os.makedirs(dump_dir, exist_ok=True)
+                np.savez(os.path.join(dump_dir, f'img{i}.npz'),
+                         **{f'silu{j}': i32(t) for j, t in enumerate(state['silu_out'])},
+                         **{f'conv{j}': i32(t) for j, t in enumerate(convs[:63])},
+                         **{f'requant{j}': i32(t) for j, t in enumerate(state['requant_out'])},
+                         dbox_cls=d)
+            if i == 0:
+                # (k, s) of all 135 requantize() calls in call order (static: scales do not depend on the image)
+                out['coeff_len'] = np.array([len(c[0]) for c in state['coeffs']])
+                out['coeff_k'] = np.concatenate([c[0] for c in state['coeffs']]).astype(np.int32)
+                out['coeff_s'] = np.concatenate([np.broadcast_to(c[1], c[0].shape) for c in state['coeffs']]).astype(np.int32)
+            if state['certify']:
+                for key in cert:
+                    cert[key] = max(cert[key], state[key]) if key.startswith('max') else cert[key] + state[key]
+            print(f'[harness] image {i}: {dt:.2f}s ncand={ncand} ndet={len(out[pre + "boxes"])}')
+    finally:
+        torch.nn.Conv2d.forward = real_conv_forward
+    out['n_images'] = np.array(len(images_u8))
+    lut = lambda d: np.array([d[key] for key in sorted(d.keys())], dtype=np.float64)
+    out['lut_sigmoid'] = lut(g['lookup']).astype(np.int32)
+    out['lut_sigmoid16'] = lut(g['lookup_final']).astype(np.int32)
+    out['lut_exp'] = lut(g['lookup_exp']).astype(np.int32)
+    out['lut_dtype'] = np.array(str(type(next(iter(g['lookup'].values())))))
+    for key, v in cert.items():
+        out['cert_' + key] = np.array(v)
+    print('[harness] exactness certificate:', cert)
+    return out, g
+
+
+def export_workload(work, k, g):
+    """Pack what the hot path reads from disk into one small npz."""
+    main_dir = f'{k}_nano'
+    sd = torch.load(os.path.join(main_dir, 'results', f'QUANT_WEIGHTS_{k}.pickle'))
+    out = {'K': np.array(k)}
+    names = []
+    for name, t in sd.items():
+        a = t.numpy()
+        assert (a == np.round(a)).all(), name
+        names.append(name)
+        if name.endswith('weight'):
+            assert np.abs(a).max() <= 127
+            out['sd/' + name] = a.astype(np.int8)
+        else:
+            out['sd/' + name] = a.astype(np.int64)
+    out['sd_keys'] = np.array(names)
+    scales = g['all_scales']
+    for name, t in scales.items():
+        out['scale/' + name] = t.numpy().astype(np.float32).reshape(-1)
+    out['scale_keys'] = np.array(sorted(scales.keys()))
+    with open(os.path.join(main_dir, 'results', 'max_a.txt')) as f:
+        out['max_a_txt'] = np.array(f.read())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--k', type=int, default=8)
+    ap.add_argument('--work', default='/tmp/ayq_work')
+    ap.add_argument('--skip-pipeline', action='store_true')
+    ap.add_argument('--n-golden', type=int, default=12)
+    ap.add_argument('--dump', default=None, help='scratch dir for full per-layer tensors (not committed)')
+    ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
+    args = ap.parse_args()
+    k = args.k
+    work = os.path.join(args.work, f'k{k}')
+    os.makedirs(os.path.join(work, 'utils'), exist_ok=True)
+    os.makedirs(os.path.join(work, 'input_data'), exist_ok=True)
+    cat = os.path.join(work, 'utils', 'cats_2_640.jpg')
+    if not os.path.exists(cat):
+        os.symlink(os.path.join(REF, 'quantisation', 'utils', 'cats_2_640.jpg'), cat)
+    pkg_root = make_overlay(work, k)
+    sys.path.insert(0, pkg_root)
+    os.chdir(work)
+    torch.set_num_threads(os.cpu_count())
+
+    calib = [synth.synth_image_u8(1000 + i).transpose(1, 2, 0).copy() for i in range(synth.N_CALIB)]
+    install_stubs(calib)
+    if not args.skip_pipeline:
+        run_pipeline(work, pkg_root, k)
+    images = [synth.synth_image_u8(s) for s in range(args.n_golden)]
+    gold, g = capture_goldens(work, pkg_root, k, images, keep_full=(0, 1, 2), dump_dir=args.dump)
+    wl = export_workload(work, k, g)
+    os.makedirs(args.out, exist_ok=True)
+    np.savez_compressed(os.path.join(args.out, f'workload_k{k}.npz'), **wl)
+    np.savez_compressed(os.path.join(args.out, f'golden_k{k}.npz'), **gold)
+    print('[harness] wrote', args.out)
+
+
+if __name__ == '__main__':
+    main()
