@@ -1,0 +1,94 @@
+"""Pins the numpy oracle (oracle/yolo_int.py) to the reference.
+
+tests/golden/golden_k*.npz was recorded by oracle/ref_harness.py from the UNMODIFIED
+reference (stage_8_torch_full_quant.py) on seeded synthetic images: sha256 of every conv
+accumulator (63), every SiLU output (57), every stand-alone requantize output (21), the
+decoded boxes / class scores, the rescale coefficients of all 135 requantize() calls, the
+three LUTs and the kept detections after q_NMS (stable tie-break)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import synth, yolo_int as Y
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def _load(golden_dir, k):
+    g = np.load(os.path.join(golden_dir, f'golden_k{k}.npz'))
+    wl = Y.Workload(os.path.join(golden_dir, f'workload_k{k}.npz'))
+    return g, wl
+
+
+@pytest.fixture(scope='module', params=[8, 6, 4])
+def pinned(request, golden_dir):
+    k = request.param
+    if not os.path.exists(os.path.join(golden_dir, f'golden_k{k}.npz')):
+        pytest.skip(f'no golden for K={k}')
+    g, wl = _load(golden_dir, k)
+    return k, g, wl, Y.OracleYolov8(wl)
+
+
+def test_luts_match_reference(pinned):
+    k, g, wl, o = pinned
+    assert np.array_equal(o.lut.astype(np.int32), g['lut_sigmoid'])
+    assert np.array_equal(o.lut16.astype(np.int32), g['lut_sigmoid16'])
+    assert np.array_equal(o.lut_exp.astype(np.int32), g['lut_exp'])
+
+
+def test_forward_matches_reference_bit_exact(pinned):
+    k, g, wl, o = pinned
+    n = min(int(g['n_images']), 4 if k == 8 else 2)
+    x = synth.to_input_array([synth.synth_image_u8(s) for s in range(n)])
+    res = o.forward(x, trace=True)
+    tr = o.trace
+    ck = np.concatenate([c[0].reshape(-1) for c in tr['coeff']])
+    cs = np.concatenate([np.broadcast_to(c[1].reshape(-1), c[0].reshape(-1).shape) for c in tr['coeff']])
+    assert np.array_equal(ck, g['coeff_k']) and np.array_equal(cs, g['coeff_s'])
+    assert len(tr['conv']) == 63 and len(tr['silu']) == 57 and len(tr['requant']) == 21
+    for i in range(n):
+        pre = f'img{i}_'
+        for name in ('conv', 'silu', 'requant'):
+            got = [sha(t[i:i + 1].astype(np.int32)) for t in tr[name]]
+            assert got == list(g[pre + name + '_sha']), (i, name)
+        assert sha(o.last['dbox'][i].astype(np.int32)) == str(g[pre + 'dbox_sha'])
+        assert sha(o.last['score'][i].astype(np.int32)) == str(g[pre + 'cls_sha'])
+        assert np.array_equal(o.last['dbox'][i].astype(np.int32), g[pre + 'dbox'])
+        b, c = res[i]
+        if b is None:
+            assert g[pre + 'boxes'].shape[0] == 0
+        else:
+            assert np.array_equal(b, g[pre + 'boxes']) and np.array_equal(c, g[pre + 'classes'])
+
+
+def test_nms_all_golden_images(pinned):
+    """q_NMS alone on the recorded dbox / score maxima: covers 0, <1000 and >1000 candidates."""
+    k, g, wl, o = pinned
+    seen = set()
+    for i in range(int(g['n_images'])):
+        pre = f'img{i}_'
+        ncand = int(g[pre + 'ncand'])
+        seen.add(0 if ncand == 0 else (1 if ncand < 1000 else 2))
+        # rebuild an (80,a) score map that has the recorded per-anchor max/argmax
+        score = np.zeros((80, 8400), np.float32)
+        score[g[pre + 'score_arg'].astype(np.int64), np.arange(8400)] = g[pre + 'score_max']
+        b, c = o.nms_one(g[pre + 'dbox'].astype(np.float32), score)
+        if b is None:
+            assert g[pre + 'boxes'].shape[0] == 0 and ncand == 0
+        else:
+            assert np.array_equal(b, g[pre + 'boxes']) and np.array_equal(c, g[pre + 'classes'])
+    if k == 8:
+        assert seen == {0, 1, 2}
+
+
+def test_requantize_edge_cases():
+    # round-half-up toward +inf, per utils/rescale_coeff_torch.py:42-44
+    assert list(Y.rsh(np.array([3, -3, 1, -1, 2, -2]), 1)) == [2, -1, 1, 0, 1, -1]
+    k, s = Y.coeffs(1.0, 1.0)
+    assert int(k[0]) == 128 and int(s[0]) == 7          # 256 overflows 8 bits -> shift decremented
+    q, _, _ = Y.requantize(np.array([[[[1000]], [[-1000]]]]), 1.0, 1.0, 8)
+    assert q.reshape(-1).tolist() == [127, -127]
