@@ -1,0 +1,587 @@
+// ayq.cu -- engine + C ABI (include/ayq.h) of the B200-native integer YOLOv8n + q_NMS path.
+//
+// The engine interprets the plan blob written by alpha_yolo_quant_b200/plan.py (plan_format.h): a list of
+// ops over 16-channel plane buffers.  It owns the packed weights / tables and the activation workspace
+// (sized for `max_batch` images); larger batches are processed as consecutive passes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ayq.h"
+#include "plan_format.h"
+#include "kernels.cuh"
+#include "conv_tc.cuh"
+
+using namespace ayq;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(-5, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct ayq_engine {
+    int device = 0;
+    PlanHeader hdr{};
+    std::vector<BufDesc> bufs;
+    std::vector<OpDesc> ops;
+    std::vector<unsigned char> host_data;
+    unsigned char* d_data = nullptr;       // data section on the device
+    int max_batch = 64;
+    int cap = 0;                           // images the workspace is sized for
+    unsigned char* ws = nullptr;
+    size_t ws_bytes = 0;
+    std::vector<size_t> buf_off;           // per buffer, for `cap`
+    size_t off_amax = 0, off_dbox = 0, off_conf = 0, off_cls = 0, off_stage = 0;
+    std::vector<KChunk*> d_kc;             // per op (device), rebuilt when cap changes
+    std::vector<int*> acc_taps;            // per tap device buffers (cap images)
+    std::vector<size_t> acc_tap_elems;     // per image
+    int conv_impl = 0;
+    int last_n = 0;
+    // host-pipeline resources
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    float* d_img[2] = {nullptr, nullptr};
+    uint8_t* d_img_u8[2] = {nullptr, nullptr};
+    float* d_dets[2] = {nullptr, nullptr};
+    int* d_counts[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_d2h[2]{};
+    int host_cap = 0;
+    bool host_u8 = false;
+    // profiling
+    bool profiling = false;
+    std::vector<float> op_ms;
+    std::vector<int> op_calls;
+    std::vector<cudaEvent_t> prof_ev;
+    TcState tc;                            // tcgen05 path state (tensor maps etc.)
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline float f_from_bits(int32_t b) { float f; memcpy(&f, &b, 4); return f; }
+
+extern "C" const char* ayq_last_error(void) { return g_err.c_str(); }
+extern "C" int ayq_version(void) { return AYQ_PLAN_VERSION; }
+
+static void free_workspace(ayq_engine* e) {
+    if (e->ws) cudaFree(e->ws);
+    e->ws = nullptr; e->ws_bytes = 0; e->cap = 0;
+    for (auto p : e->d_kc) if (p) cudaFree(p);
+    e->d_kc.clear();
+    for (auto p : e->acc_taps) if (p) cudaFree(p);
+    e->acc_taps.clear();
+    tc_release(e->tc);
+}
+
+static int ensure_workspace(ayq_engine* e, int n) {
+    if (n <= e->cap) return 0;
+    free_workspace(e);
+    const int cap = n;
+    size_t off = 0;
+    e->buf_off.resize(e->bufs.size());
+    for (size_t i = 0; i < e->bufs.size(); ++i) {
+        const BufDesc& b = e->bufs[i];
+        e->buf_off[i] = off;
+        off = align_up(off + (size_t)b.nplanes * cap * b.H * b.W * 16 * b.elem_bytes, 1024);
+    }
+    const int A = e->hdr.n_anchors;
+    e->off_amax = off; off = align_up(off + sizeof(float) * cap, 1024);
+    e->off_dbox = off; off = align_up(off + sizeof(float4) * (size_t)cap * A, 1024);
+    e->off_conf = off; off = align_up(off + sizeof(int) * (size_t)cap * A, 1024);
+    e->off_cls = off;  off = align_up(off + sizeof(int) * (size_t)cap * A, 1024);
+    CK(cudaMalloc(&e->ws, off));
+    CK(cudaMemset(e->ws, 0, off));
+    e->ws_bytes = off;
+    e->cap = cap;
+    // resolve K-chunk tables and accumulator taps
+    e->d_kc.assign(e->ops.size(), nullptr);
+    int ntaps = 0;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const int32_t* f = e->ops[i].f;
+        int tap = -1; size_t elems = 0;
+        if (f[0] == OP_CONV) {
+            const int nkc = f[CF_NKC];
+            const int32_t* src = (const int32_t*)(e->host_data.data() + f[CF_KC_OFF]);
+            const int pad = f[CF_KSIZE] / 2;
+            std::vector<KChunk> kc(nkc);
+            for (int k = 0; k < nkc; ++k) {
+                kc[k].off = (long long)e->buf_off[src[4 * k]];
+                kc[k].plane = src[4 * k + 1];
+                kc[k].dy = src[4 * k + 2] - pad;
+                kc[k].dx = src[4 * k + 3] - pad;
+                kc[k].pad_ = 0;
+            }
+            CK(cudaMalloc(&e->d_kc[i], sizeof(KChunk) * nkc));
+            CK(cudaMemcpy(e->d_kc[i], kc.data(), sizeof(KChunk) * nkc, cudaMemcpyHostToDevice));
+            tap = f[CF_ACC_TAP];
+            elems = (size_t)f[CF_COUT] * f[CF_HOUT] * f[CF_WOUT];
+        } else if (f[0] == OP_CONV_P1) {
+            tap = f[P1_ACC_TAP];
+            elems = (size_t)16 * f[P1_HOUT] * f[P1_WOUT];
+        }
+        if (tap >= 0) {
+            if ((int)e->acc_taps.size() <= tap) { e->acc_taps.resize(tap + 1, nullptr); e->acc_tap_elems.resize(tap + 1, 0); }
+            CK(cudaMalloc(&e->acc_taps[tap], elems * cap * sizeof(int)));
+            e->acc_tap_elems[tap] = elems;
+            ++ntaps;
+        }
+    }
+    (void)ntaps;
+    return 0;
+}
+
+extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_handle* out) {
+    if (!plan_blob || !out || nbytes < sizeof(PlanHeader)) return fail(-22, "ayq_create: bad arguments");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(-19, "ayq_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(-22, "ayq_create: device %d out of range (%d devices)", device, ndev);
+    const unsigned char* p = (const unsigned char*)plan_blob;
+    PlanHeader h;
+    memcpy(&h, p, sizeof h);
+    if (h.magic != AYQ_MAGIC) return fail(-22, "ayq_create: bad magic 0x%x", h.magic);
+    if (h.version != AYQ_PLAN_VERSION) return fail(-22, "ayq_create: plan version %u, library %d", h.version, AYQ_PLAN_VERSION);
+    if (h.K < 2 || h.K > 9) return fail(-22, "ayq_create: unsupported bit width K=%d (2..9)", h.K);
+    if (h.data_off + h.data_bytes > nbytes || h.ops_off + (uint64_t)h.n_ops * sizeof(OpDesc) > nbytes ||
+        h.bufs_off + (uint64_t)h.n_bufs * sizeof(BufDesc) > nbytes)
+        return fail(-22, "ayq_create: truncated plan (%zu bytes)", nbytes);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(-19, "ayq_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    ayq_engine* e = new ayq_engine();
+    e->device = device;
+    e->hdr = h;
+    e->bufs.resize(h.n_bufs);
+    memcpy(e->bufs.data(), p + h.bufs_off, sizeof(BufDesc) * h.n_bufs);
+    e->ops.resize(h.n_ops);
+    memcpy(e->ops.data(), p + h.ops_off, sizeof(OpDesc) * h.n_ops);
+    e->host_data.assign(p + h.data_off, p + h.data_off + h.data_bytes);
+    if (cudaMalloc(&e->d_data, h.data_bytes) != cudaSuccess ||
+        cudaMemcpy(e->d_data, e->host_data.data(), h.data_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete e;
+        return fail(-12, "ayq_create: cannot upload %llu bytes of plan data", (unsigned long long)h.data_bytes);
+    }
+    cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM);
+    tc_init(e->tc);
+    e->op_ms.assign(h.n_ops + 1, 0.f);
+    e->op_calls.assign(h.n_ops + 1, 0);
+    *out = e;
+    return 0;
+}
+
+extern "C" int ayq_destroy(ayq_handle e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    free_workspace(e);
+    if (e->d_data) cudaFree(e->d_data);
+    for (int i = 0; i < 2; ++i) {
+        if (e->d_img[i]) cudaFree(e->d_img[i]);
+        if (e->d_img_u8[i]) cudaFree(e->d_img_u8[i]);
+        if (e->d_dets[i]) cudaFree(e->d_dets[i]);
+        if (e->d_counts[i]) cudaFree(e->d_counts[i]);
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+        if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+    }
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    delete e;
+    return 0;
+}
+
+extern "C" int ayq_set_max_batch(ayq_handle e, int max_batch) {
+    if (!e || max_batch < 1 || max_batch > 4096) return fail(-22, "ayq_set_max_batch: 1..4096");
+    e->max_batch = max_batch;
+    return 0;
+}
+extern "C" size_t ayq_workspace_bytes(ayq_handle e) { return e ? e->ws_bytes : 0; }
+extern "C" int ayq_set_conv_impl(ayq_handle e, int impl) {
+    if (!e || impl < 0 || impl > 1) return fail(-22, "ayq_set_conv_impl: 0 (dp4a) or 1 (tcgen05)");
+    e->conv_impl = impl;
+    return 0;
+}
+extern "C" int ayq_set_profiling(ayq_handle e, int enabled) {
+    if (!e) return fail(-22, "null handle");
+    e->profiling = enabled != 0;
+    if (e->profiling && e->prof_ev.empty()) {
+        e->prof_ev.resize(e->ops.size() + 2);
+        for (auto& ev : e->prof_ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail(-5, "cudaEventCreate");
+    }
+    std::fill(e->op_ms.begin(), e->op_ms.end(), 0.f);
+    std::fill(e->op_calls.begin(), e->op_calls.end(), 0);
+    return 0;
+}
+extern "C" int ayq_get_op_times(ayq_handle e, float* ms, int32_t* calls, int cap) {
+    if (!e) return fail(-22, "null handle");
+    const int n = (int)e->op_ms.size();
+    for (int i = 0; i < n && i < cap; ++i) { ms[i] = e->op_ms[i]; calls[i] = e->op_calls[i]; }
+    return n;
+}
+extern "C" int ayq_launches_per_pass(ayq_handle e) {
+    if (!e) return fail(-22, "null handle");
+    return (int)e->ops.size() + 1;          // + the abs-max reduction; the memset node is not a kernel
+}
+
+// ---- one pass over n <= cap images ---------------------------------------------------------------------
+static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
+    const int32_t* f = e->ops[opi].f;
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.kc = e->d_kc[opi];
+    a.nkc = f[CF_NKC];
+    a.ws = (const int8_t*)e->ws;
+    a.in_plane_bytes = (size_t)n * f[CF_HIN] * f[CF_WIN] * 16;
+    a.w = (const int8_t*)(e->d_data + f[CF_W_OFF]);
+    a.bias = (const int*)(e->d_data + f[CF_BIAS_OFF]);
+    a.tab = (const float*)(e->d_data + f[CF_TAB_OFF]);
+    a.lut = (const float*)(e->d_data + f[CF_LUT_OFF]);
+    a.n = n; a.Hin = f[CF_HIN]; a.Win = f[CF_WIN]; a.Hout = f[CF_HOUT]; a.Wout = f[CF_WOUT];
+    a.stride = f[CF_STRIDE]; a.cout = f[CF_COUT]; a.epi = f[CF_EPI]; a.M = f[CF_CLAMP];
+    a.nout = f[CF_NOUT];
+    for (int o = 0; o < a.nout; ++o) {
+        const int32_t* of = f + CF_OUT0 + CF_OUT_STRIDE * o;
+        const BufDesc& b = e->bufs[of[0]];
+        a.out[o].base = e->ws + e->buf_off[of[0]] + (size_t)of[1] * n * b.H * b.W * 16 * b.elem_bytes;
+        a.out[o].mode = of[2];
+        a.out[o].k = f_from_bits(of[3]);
+        a.out[o].inv = f_from_bits(of[4]);
+        a.out[o].up = of[5];
+    }
+    a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
+    if (e->conv_impl == 1) {
+        int rc = tc_launch_conv(e->tc, a, f, st);
+        if (rc == 0) return 0;
+        if (rc != 1) return fail(-5, "tcgen05 conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
+        // rc == 1: shape not covered by the tcgen05 kernel -> CUDA-core kernel below
+    }
+    const size_t npix = (size_t)n * a.Hout * a.Wout;
+    const unsigned gx = (unsigned)((npix + 127) / 128);
+    const size_t lut_bytes = (size_t)(2 * a.M + 1) * 4;
+    if (a.cout % 32 == 0) {
+        conv_dp4a_kernel<32><<<dim3(gx, a.cout / 32), 128, (size_t)a.nkc * 32 * 16 + lut_bytes, st>>>(a);
+    } else {
+        conv_dp4a_kernel<16><<<dim3(gx, a.cout / 16), 128, (size_t)a.nkc * 16 * 16 + lut_bytes, st>>>(a);
+    }
+    return 0;
+}
+
+static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
+    const int H = e->hdr.img_h, W = e->hdr.img_w, A = e->hdr.n_anchors;
+    float* amax = (float*)(e->ws + e->off_amax);
+    float4* dbox = (float4*)(e->ws + e->off_dbox);
+    int* conf = (int*)(e->ws + e->off_conf);
+    int* cls = (int*)(e->ws + e->off_cls);
+    const bool prof = e->profiling;
+    int pe = 0;
+    if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
+    CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
+    absmax_kernel<<<dim3(64, n), 256, 0, st>>>(img, amax, (size_t)3 * H * W);
+    if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const int32_t* f = e->ops[i].f;
+        switch (f[0]) {
+        case OP_CONV_P1: {
+            P1Args a;
+            a.img = img; a.amax = amax;
+            a.w = (const int8_t*)(e->d_data + f[P1_W_OFF]);
+            a.bias = (const int*)(e->d_data + f[P1_BIAS_OFF]);
+            a.tab = (const float*)(e->d_data + f[P1_TAB_OFF]);
+            a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
+            a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
+            a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
+            a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
+            const size_t npix = (size_t)n * a.Hout * a.Wout;
+            conv_p1_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(a);
+            break;
+        }
+        case OP_CONV: {
+            int rc = launch_conv(e, (int)i, n, st);
+            if (rc) return rc;
+            break;
+        }
+        case OP_POOL: {
+            const BufDesc& ib = e->bufs[f[PL_IN_BUF]];
+            const BufDesc& ob = e->bufs[f[PL_OUT_BUF]];
+            const size_t ppx = (size_t)n * f[PL_H] * f[PL_W] * 16;
+            const int8_t* in = (const int8_t*)(e->ws + e->buf_off[f[PL_IN_BUF]]) + (size_t)f[PL_IN_PLANE0] * ppx;
+            int8_t* out = (int8_t*)(e->ws + e->buf_off[f[PL_OUT_BUF]]) + (size_t)f[PL_OUT_PLANE0] * ppx;
+            (void)ib; (void)ob;
+            sppf_pool_kernel<<<dim3(f[PL_NPLANES], n), 256, (size_t)f[PL_H] * f[PL_W] * 16 * 2, st>>>(in, out, n, f[PL_H], f[PL_W], f[PL_NPLANES]);
+            break;
+        }
+        case OP_HEAD: {
+            HeadArgs a;
+            for (int l = 0; l < 3; ++l) {
+                a.box[l] = (const int8_t*)(e->ws + e->buf_off[f[HD_BOX_BUF0 + l]]);
+                a.cls[l] = (const int16_t*)(e->ws + e->buf_off[f[HD_CLS_BUF0 + l]]);
+            }
+            a.lut_exp = (const float*)(e->d_data + f[HD_LUT_EXP_OFF]);
+            a.lut16 = (const int16_t*)(e->d_data + f[HD_LUT16_OFF]);
+            a.dflw = (const int*)(e->d_data + f[HD_DFLW_OFF]);
+            a.anchors = (const int*)(e->d_data + f[HD_ANCH_OFF]);
+            a.kd = f_from_bits(f[HD_KD]); a.id = f_from_bits(f[HD_ID]);
+            a.n = n; a.K = e->hdr.K; a.A = A;
+            a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.dbox_cls = dbox_cls;
+            head_kernel<<<(unsigned)(((size_t)n * A + 127) / 128), 128, 0, st>>>(a);
+            break;
+        }
+        case OP_NMS: {
+            NmsArgs a;
+            a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.boxes = nullptr; a.scores = nullptr; a.n = n; a.A = A; a.mode = 0; a.max_keep = NMS_MAXDET; a.dets = dets; a.counts = counts;
+            nms_kernel<<<n, NMS_THREADS, NMS_SMEM, st>>>(a);
+            break;
+        }
+        default:
+            return fail(-22, "plan op %zu has unknown kind %d", i, f[0]);
+        }
+        if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
+    }
+    CK(cudaGetLastError());
+    if (prof) {
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i + 1 < pe; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e->prof_ev[i], e->prof_ev[i + 1]));
+            e->op_ms[i] += ms;
+            e->op_calls[i] += 1;
+        }
+    }
+    e->last_n = n;
+    return 0;
+}
+
+extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream) {
+    if (!e || !img || !dets || !counts || n < 0) return fail(-22, "ayq_forward: bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mb = e->max_batch;
+    int rc = ensure_workspace(e, n < mb ? n : mb);
+    if (rc) return rc;
+    const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
+    for (int i0 = 0; i0 < n; i0 += mb) {
+        const int m = (n - i0) < mb ? (n - i0) : mb;
+        rc = run_pass(e, img + (size_t)i0 * img_elems, m, dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
+                      dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, counts + i0, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---- host-buffer entry: double-buffered H2D / compute / D2H --------------------------------------------
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t total) {
+    // ToTensor(): u8 / 255 in fp32 (stage_8_torch.py:985-990)
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (size_t)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < total) {
+            const uchar4 v = *(const uchar4*)(src + i);
+            *(float4*)(dst + i) = make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f),
+                                              __fdiv_rn((float)v.z, 255.f), __fdiv_rn((float)v.w, 255.f));
+        } else {
+            for (size_t j = i; j < total; ++j) dst[j] = __fdiv_rn((float)src[j], 255.f);
+        }
+    }
+}
+
+static int ensure_host_pipeline(ayq_engine* e, int m, bool u8) {
+    if (!e->s_copy) {
+        CK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    if (m > e->host_cap || (u8 && !e->d_img_u8[0])) {
+        const int cap = m > e->host_cap ? m : e->host_cap;
+        const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
+        for (int i = 0; i < 2; ++i) {
+            if (cap > e->host_cap) {
+                if (e->d_img[i]) cudaFree(e->d_img[i]);
+                if (e->d_dets[i]) cudaFree(e->d_dets[i]);
+                if (e->d_counts[i]) cudaFree(e->d_counts[i]);
+                if (e->d_img_u8[i]) { cudaFree(e->d_img_u8[i]); e->d_img_u8[i] = nullptr; }
+                CK(cudaMalloc(&e->d_img[i], img_elems * cap * sizeof(float)));
+                CK(cudaMalloc(&e->d_dets[i], (size_t)cap * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float)));
+                CK(cudaMalloc(&e->d_counts[i], (size_t)cap * sizeof(int)));
+            }
+            if (u8 && !e->d_img_u8[i]) CK(cudaMalloc(&e->d_img_u8[i], img_elems * cap));
+        }
+        e->host_cap = cap;
+    }
+    return 0;
+}
+
+static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n, float* dets_host, int32_t* counts_host) {
+    if (!e || !img_host || !dets_host || !counts_host || n < 0) return fail(-22, "ayq_forward_host: bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    const int mb = e->max_batch;
+    const int m_max = n < mb ? n : mb;
+    int rc = ensure_workspace(e, m_max);
+    if (rc) return rc;
+    rc = ensure_host_pipeline(e, m_max, u8);
+    if (rc) return rc;
+    const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
+    int slot = 0, pass = 0;
+    for (int i0 = 0; i0 < n; i0 += mb, ++pass, slot ^= 1) {
+        const int m = (n - i0) < mb ? (n - i0) : mb;
+        if (pass >= 2) {                       // slot reuse: its previous results must have left the device
+            CK(cudaStreamWaitEvent(e->s_copy, e->ev_d2h[slot], 0));
+            CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));
+        }
+        if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
+        else CK(cudaMemcpyAsync(e->d_img[slot], (const float*)img_host + (size_t)i0 * img_elems, img_elems * m * sizeof(float), cudaMemcpyHostToDevice, e->s_copy));
+        CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
+        CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
+        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));   // d_dets[slot] still draining
+        if (u8) u8_to_f32_kernel<<<1184, 256, 0, e->s_comp>>>(e->d_img_u8[slot], e->d_img[slot], img_elems * m);
+        rc = run_pass(e, e->d_img[slot], m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
+        if (rc) return rc;
+        CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
+        // D2H on the copy stream keeps the compute stream free for the next pass
+        CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));
+        CK(cudaMemcpyAsync(dets_host + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, e->d_dets[slot],
+                           (size_t)m * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, e->s_copy));
+        CK(cudaMemcpyAsync(counts_host + i0, e->d_counts[slot], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, e->s_copy));
+        CK(cudaEventRecord(e->ev_d2h[slot], e->s_copy));
+    }
+    CK(cudaStreamSynchronize(e->s_copy));
+    CK(cudaStreamSynchronize(e->s_comp));
+    return 0;
+}
+
+extern "C" int ayq_forward_host(ayq_handle e, const float* img_host, int n, float* dets_host, int32_t* counts_host) {
+    return forward_host_impl(e, img_host, false, n, dets_host, counts_host);
+}
+extern "C" int ayq_forward_host_u8(ayq_handle e, const uint8_t* img_host, int n, float* dets_host, int32_t* counts_host) {
+    return forward_host_impl(e, img_host, true, n, dets_host, counts_host);
+}
+
+// ---- taps ---------------------------------------------------------------------------------------------
+extern "C" int ayq_buffer_shape(ayq_handle e, int buf, int* channels, int* height, int* width) {
+    if (!e || buf < 0 || buf >= (int)e->bufs.size()) return fail(-22, "ayq_buffer_shape: bad buffer %d", buf);
+    if (channels) *channels = e->bufs[buf].nplanes * 16;
+    if (height) *height = e->bufs[buf].H;
+    if (width) *width = e->bufs[buf].W;
+    return 0;
+}
+extern "C" int ayq_export_buffer(ayq_handle e, int buf, int n, int32_t* dst, void* stream) {
+    if (!e || buf < 0 || buf >= (int)e->bufs.size() || !dst) return fail(-22, "ayq_export_buffer: bad arguments");
+    if (n != e->last_n) return fail(-22, "ayq_export_buffer: n=%d but the last pass had %d images", n, e->last_n);
+    const BufDesc& b = e->bufs[buf];
+    export_planes_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(e->ws + e->buf_off[buf], b.elem_bytes, b.nplanes, n, b.H, b.W, dst);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_export_acc_tap(ayq_handle e, int tap, int n, int32_t* dst, void* stream) {
+    if (!e || tap < 0 || tap >= (int)e->acc_taps.size() || !dst) return fail(-22, "ayq_export_acc_tap: bad tap %d (plan compiled without taps?)", tap);
+    if (n != e->last_n) return fail(-22, "ayq_export_acc_tap: n=%d but the last pass had %d images", n, e->last_n);
+    CK(cudaMemcpyAsync(dst, e->acc_taps[tap], e->acc_tap_elems[tap] * n * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+// ---- unit-level layer library -------------------------------------------------------------------------
+static inline unsigned grid_for(size_t total) {
+    size_t g = (total + 255) / 256;
+    return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+extern "C" int ayq_requantize_f32(const float* x, float* y, const float* k, const float* inv2s, int per_channel,
+                                  int n, int c, int hw, int bits, void* stream) {
+    if (!x || !y || !k || !inv2s || bits < 2 || bits > 24) return fail(-22, "ayq_requantize_f32: bad arguments");
+    const size_t total = (size_t)n * c * hw;
+    if (!total) return 0;
+    requantize_f32_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, k, inv2s, per_channel, c, hw, total, (1 << (bits - 1)) - 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_silu_f32(const float* acc, float* y, const float* tab, const float* lut, int n, int c, int hw, int bits, void* stream) {
+    if (!acc || !y || !tab || !lut || bits < 2 || bits > 16) return fail(-22, "ayq_silu_f32: bad arguments");
+    const size_t total = (size_t)n * c * hw;
+    if (!total) return 0;
+    silu_f32_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(acc, y, tab, lut, c, hw, total, (1 << (bits - 1)) - 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_lut_f32(const float* x, float* y, const float* lut, int key_min, int key_max, size_t count, void* stream) {
+    if (!x || !y || !lut || key_max < key_min) return fail(-22, "ayq_lut_f32: bad arguments");
+    if (!count) return 0;
+    lut_f32_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, y, lut, key_min, key_max, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_absmax_f32(const float* x, float* out, int n, size_t per_image, void* stream) {
+    if (!x || !out || n < 0) return fail(-22, "ayq_absmax_f32: bad arguments");
+    if (!n) return 0;
+    CK(cudaMemsetAsync(out, 0, sizeof(float) * n, (cudaStream_t)stream));
+    if (!per_image) return 0;
+    size_t blocks = (per_image / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 64) blocks = 64;
+    absmax_kernel<<<dim3((unsigned)blocks, n), 256, 0, (cudaStream_t)stream>>>(x, out, per_image);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_quant_input_f32(const float* x, float* y, float* amax, float* scales, int n, size_t per_image, int bits, void* stream) {
+    if (!x || !y || !amax || !scales || bits < 2 || bits > 16) return fail(-22, "ayq_quant_input_f32: bad arguments");
+    int rc = ayq_absmax_f32(x, amax, n, per_image, stream);
+    if (rc) return rc;
+    const size_t total = per_image * n;
+    if (!total) return 0;
+    quant_input_f32_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, amax, scales, per_image, n, (1 << (bits - 1)) - 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_nms(ayq_handle e, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream) {
+    if (!e || !dbox_cls || !dets || !counts || n < 0) return fail(-22, "ayq_nms: bad arguments");
+    if (!n) return 0;
+    CK(cudaSetDevice(e->device));
+    const int A = e->hdr.n_anchors;
+    const int mb = e->max_batch;
+    int rc = ensure_workspace(e, n < mb ? n : mb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += e->cap) {
+        const int m = (n - i0) < e->cap ? (n - i0) : e->cap;
+        float4* dbox = (float4*)(e->ws + e->off_dbox);
+        int* conf = (int*)(e->ws + e->off_conf);
+        int* cls = (int*)(e->ws + e->off_cls);
+        pred_to_cand_kernel<<<(unsigned)(((size_t)m * A + 127) / 128), 128, 0, st>>>(dbox_cls + (size_t)i0 * 84 * A, m, A, dbox, conf, cls);
+        NmsArgs a;
+        a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.boxes = nullptr; a.scores = nullptr; a.n = m; a.A = A; a.mode = 0; a.max_keep = NMS_MAXDET;
+        a.dets = dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE; a.counts = counts + i0;
+        nms_kernel<<<m, NMS_THREADS, NMS_SMEM, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ayq_nms_boxes(const float* boxes, const float* scores, int nb, float* keep, int32_t* count, void* stream) {
+    if (!boxes || !scores || !keep || !count || nb < 0 || nb > NMS_SORT_N) return fail(-22, "ayq_nms_boxes: 0 <= nb <= %d", NMS_SORT_N);
+    if (nb == 0) { CK(cudaMemsetAsync(count, 0, sizeof(int), (cudaStream_t)stream)); return 0; }
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM)); attr_set = true; }
+    NmsArgs a;
+    a.dbox = nullptr; a.conf = nullptr; a.cls_id = nullptr; a.boxes = boxes; a.scores = scores;
+    a.n = 1; a.A = nb; a.mode = 1; a.max_keep = NMS_TOPK; a.dets = keep; a.counts = count;
+    nms_kernel<<<1, NMS_THREADS, NMS_SMEM, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,582 @@
+// kernels.cuh -- CUDA-core kernels of the integer YOLOv8n engine (sm_100a).
+//   conv_dp4a_kernel   generic quantised conv over 16-channel plane segments, dp4a, fused epilogue
+//   conv_p1_kernel     Conv_P1 on the fp32 image with the fused per-image input quantiser
+//   absmax_kernel      per-image max|x| (quant_matrix / save_max_a)
+//   sppf_pool_kernel   three cascaded MaxPool2d(5,1,2)
+//   head_kernel        DFL decode + 16-bit class scores (max / first argmax)
+//   nms_kernel         coord_quant + nms_quant + clip_boxes, one CTA per image
+// The tcgen05 convolution lives in conv_tc.cuh; both share ConvArgs and the epilogue below.
+#pragma once
+#include "fixedpoint.cuh"
+
+namespace ayq {
+
+struct KChunk { long long off; int plane, dy, dx, pad_; };   // workspace byte offset of the buffer, plane, tap offset minus padding
+struct OutSpec { void* base; int mode; float k, inv; int up; };
+
+struct ConvArgs {
+    const KChunk* kc; int nkc;
+    const int8_t* ws;           // activation workspace base
+    size_t in_plane_bytes;      // n * Hin * Win * 16
+    const int8_t* w;            // [nkc_pad][cout][16]
+    const int* bias; const float* tab; const float* lut;
+    int n, Hin, Win, Hout, Wout, stride, cout, epi, M;
+    int nout; OutSpec out[3];
+    int* acc_tap;               // NCHW int32 (n, cout, Hout, Wout) or nullptr
+};
+
+// ---- shared epilogue: 16 consecutive output channels [c0, c0+16) of one output pixel -----------------
+// acc[] already holds the bias.  pix = (img*Hout + oy)*Wout + ox.
+__device__ __forceinline__ void epilogue16(const ConvArgs& a, const int* acc, int c0, int img, int oy, int ox,
+                                           const float* __restrict__ lut_s) {
+    const int M = a.M;
+    const int cout = a.cout;
+    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
+    const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+    if (a.acc_tap) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            a.acc_tap[(((size_t)img * cout + c0 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
+    }
+    const float* tab = a.tab;
+    if (a.epi == 0) {                 // EPI_SILU
+        int r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            int c = c0 + j;
+            r[j] = silu_q(acc[j], __ldg(tab + c), __ldg(tab + cout + c), __ldg(tab + 2 * cout + c), __ldg(tab + 3 * cout + c), lut_s, M);
+        }
+        for (int o = 0; o < a.nout; ++o) {
+            const OutSpec& os = a.out[o];
+            uint32_t wd[4];
+            if (os.mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    wd[j] = pack4(requant((float)r[4 * j], os.k, os.inv, M), requant((float)r[4 * j + 1], os.k, os.inv, M),
+                                  requant((float)r[4 * j + 2], os.k, os.inv, M), requant((float)r[4 * j + 3], os.k, os.inv, M));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wd[j] = pack4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+            uint4 v = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            int8_t* base = (int8_t*)os.base;
+            if (!os.up) {
+                *(uint4*)(base + ((size_t)(c0 >> 4) * npix + pix) * 16) = v;
+            } else {             // nn.Upsample(None, 2, 'nearest') then requantize (:900-903): 2x2 replicate
+                const int H2 = a.Hout * 2, W2 = a.Wout * 2;
+                const size_t np2 = npix * 4;
+                size_t p00 = ((size_t)img * H2 + 2 * oy) * W2 + 2 * ox;
+                int8_t* pl = base + (size_t)(c0 >> 4) * np2 * 16;
+                *(uint4*)(pl + p00 * 16) = v;
+                *(uint4*)(pl + (p00 + 1) * 16) = v;
+                *(uint4*)(pl + (p00 + W2) * 16) = v;
+                *(uint4*)(pl + (p00 + W2 + 1) * 16) = v;
+            }
+        }
+    } else if (a.epi == 1) {          // EPI_REQUANT8
+        uint32_t wd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int q[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                int c = c0 + 4 * j + t;
+                q[t] = requant(__int2float_rn(acc[4 * j + t]), __ldg(tab + c), __ldg(tab + cout + c), M);
+            }
+            wd[j] = pack4(q[0], q[1], q[2], q[3]);
+        }
+        *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    } else {                          // EPI_REQUANT16
+        uint32_t wd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int c = c0 + 2 * j;
+            int q0 = requant(__int2float_rn(acc[2 * j]), __ldg(tab + c), __ldg(tab + cout + c), M);
+            int q1 = requant(__int2float_rn(acc[2 * j + 1]), __ldg(tab + c + 1), __ldg(tab + cout + c + 1), M);
+            wd[j] = (uint32_t)(q0 & 0xffff) | ((uint32_t)(q1 & 0xffff) << 16);
+        }
+        uint4* dst = (uint4*)((int16_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16);
+        dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+    }
+}
+
+// ---- generic dp4a convolution -------------------------------------------------------------------------
+// grid (ceil(n*Hout*Wout / 128), cout / NC), block 128: one output pixel x NC output channels per thread.
+template <int NC>
+__global__ void __launch_bounds__(128) conv_dp4a_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* sW = (uint4*)smem_raw;                                 // [nkc][NC] 16-byte rows
+    float* lut_s = (float*)(smem_raw + (size_t)a.nkc * NC * 16);  // [2M+1]
+    const int c0 = blockIdx.y * NC;
+    for (int i = threadIdx.x; i < a.nkc * NC; i += 128) {
+        int kc = i / NC, j = i % NC;
+        sW[i] = *(const uint4*)(a.w + ((size_t)kc * a.cout + c0 + j) * 16);
+    }
+    if (a.epi == 0)
+        for (int i = threadIdx.x; i < 2 * a.M + 1; i += 128) lut_s[i] = a.lut[i];
+    __syncthreads();
+    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
+    const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (p >= npix) return;
+    const int ox = (int)(p % a.Wout);
+    const int oy = (int)((p / a.Wout) % a.Hout);
+    const int img = (int)(p / ((size_t)a.Wout * a.Hout));
+    int acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = __ldg(a.bias + c0 + j);
+    const int iy0 = oy * a.stride, ix0 = ox * a.stride;
+    for (int kc = 0; kc < a.nkc; ++kc) {
+        const KChunk k = a.kc[kc];
+        const int iy = iy0 + k.dy, ix = ix0 + k.dx;
+        if ((unsigned)iy >= (unsigned)a.Hin || (unsigned)ix >= (unsigned)a.Win) continue;   // zero padding
+        const int4 v = __ldg((const int4*)(a.ws + k.off + (size_t)k.plane * a.in_plane_bytes + (((size_t)img * a.Hin + iy) * a.Win + ix) * 16));
+        const uint4* wr = sW + kc * NC;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const uint4 wv = wr[j];
+            int s = acc[j];
+            s = __dp4a(v.x, (int)wv.x, s);
+            s = __dp4a(v.y, (int)wv.y, s);
+            s = __dp4a(v.z, (int)wv.z, s);
+            s = __dp4a(v.w, (int)wv.w, s);
+            acc[j] = s;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NC / 16; ++g) epilogue16(a, acc + 16 * g, c0 + 16 * g, img, oy, ox, lut_s);
+}
+
+// ---- Conv_P1 + quant_matrix ---------------------------------------------------------------------------
+struct P1Args {
+    const float* img;           // (n,3,H,W) fp32
+    const float* amax;          // (n) per-image max|x|
+    const int8_t* w;            // [16][32]
+    const int* bias; const float* tab; const float* lut;
+    int n, H, W, Hout, Wout, M;
+    int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
+    int* acc_tap;
+};
+
+__global__ void __launch_bounds__(128) conv_p1_kernel(const P1Args a) {
+    __shared__ uint4 sW[16][2];
+    __shared__ float lut_s[1024];
+    if (threadIdx.x < 32) sW[threadIdx.x >> 1][threadIdx.x & 1] = ((const uint4*)a.w)[threadIdx.x];
+    for (int i = threadIdx.x; i < 2 * a.M + 1; i += 128) lut_s[i] = a.lut[i];
+    __syncthreads();
+    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
+    const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (p >= npix) return;
+    const int ox = (int)(p % a.Wout);
+    const int oy = (int)((p / a.Wout) % a.Hout);
+    const int img = (int)(p / ((size_t)a.Wout * a.Hout));
+    // quant_matrix: a = max|x|, s = fl32(M / a), q = rint(fl32(clip(x) * s))   (utils/quant_matrix_torch.py:57-70)
+    const float amax = a.amax[img];
+    const float s = __fdiv_rn((float)a.M, amax);
+    int q[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) q[i] = 0;
+    const float* base = a.img + (size_t)img * 3 * a.H * a.W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = 2 * ox + kx - 1;
+            const bool ok = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W && amax > 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = ok ? __ldg(base + ((size_t)c * a.H + iy) * a.W + ix) : 0.f;
+                x = fminf(fmaxf(x, -amax), amax);
+                q[(ky * 3 + kx) * 3 + c] = ok ? __float2int_rn(__fmul_rn(x, s)) : 0;
+            }
+        }
+    }
+    int wd[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) wd[i] = (int)pack4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+    int acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint4 w0 = sW[j][0], w1 = sW[j][1];
+        int sacc = __ldg(a.bias + j);
+        sacc = __dp4a(wd[0], (int)w0.x, sacc);
+        sacc = __dp4a(wd[1], (int)w0.y, sacc);
+        sacc = __dp4a(wd[2], (int)w0.z, sacc);
+        sacc = __dp4a(wd[3], (int)w0.w, sacc);
+        sacc = __dp4a(wd[4], (int)w1.x, sacc);
+        sacc = __dp4a(wd[5], (int)w1.y, sacc);
+        sacc = __dp4a(wd[6], (int)w1.z, sacc);
+        acc[j] = sacc;
+    }
+    if (a.acc_tap) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a.acc_tap[(((size_t)img * 16 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
+    }
+    int r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        r[j] = silu_q(acc[j], __ldg(a.tab + j), __ldg(a.tab + 16 + j), __ldg(a.tab + 32 + j), __ldg(a.tab + 48 + j), lut_s, a.M);
+    *(uint4*)(a.out + p * 16) = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]),
+                                           pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
+}
+
+// ---- per-image abs-max --------------------------------------------------------------------------------
+// grid (blocks, n); out[] must be zeroed first.  |x| >= 0 so the float bit pattern orders like an int.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, float* __restrict__ out, size_t per_image) {
+    const float* base = x + (size_t)blockIdx.y * per_image;
+    float m = 0.f;
+    const size_t nvec = per_image / 4;
+    const bool aligned = (((uintptr_t)base) & 15) == 0;
+    if (aligned) {
+        const float4* b4 = (const float4*)base;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+            float4 v = __ldg(b4 + i);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        for (size_t i = nvec * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < per_image; i += (size_t)gridDim.x * 256)
+            m = fmaxf(m, fabsf(base[i]));
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < per_image; i += (size_t)gridDim.x * 256)
+            m = fmaxf(m, fabsf(base[i]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
+        atomicMax((int*)out + blockIdx.y, __float_as_int(m));
+    }
+}
+
+// ---- SPPF: three cascaded 5x5 stride-1 max pools (padding = -inf, i.e. window clipped to the map) -----
+// grid (nplanes, n), block 256.  in/out: plane buffers (plane, n, H, W, 16) int8.
+__global__ void __launch_bounds__(256) sppf_pool_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out,
+                                                        int n, int H, int W, int nplanes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* A = (unsigned*)smem_raw;                  // [H*W*4]
+    unsigned* B = A + H * W * 4;
+    const int pl = blockIdx.x, img = blockIdx.y;
+    const size_t plane_px = (size_t)n * H * W;
+    const unsigned* src = (const unsigned*)(in + ((size_t)pl * plane_px + (size_t)img * H * W) * 16);
+    const int nw = H * W * 4;
+    for (int i = threadIdx.x; i < nw; i += 256) A[i] = src[i];
+    __syncthreads();
+    for (int stage = 0; stage < 3; ++stage) {
+        for (int i = threadIdx.x; i < nw; i += 256) {   // row pass: max over x-2..x+2
+            const int wq = i & 3, px = i >> 2, x = px % W, y = px / W;
+            unsigned m = A[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                const int xx = x + d;
+                if (d != 0 && xx >= 0 && xx < W) m = __vmaxs4(m, A[((y * W + xx) << 2) + wq]);
+            }
+            B[i] = m;
+        }
+        __syncthreads();
+        unsigned* dst = (unsigned*)(out + ((size_t)(stage * nplanes + pl) * plane_px + (size_t)img * H * W) * 16);
+        for (int i = threadIdx.x; i < nw; i += 256) {   // column pass
+            const int wq = i & 3, px = i >> 2, x = px % W, y = px / W;
+            unsigned m = B[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                const int yy = y + d;
+                if (d != 0 && yy >= 0 && yy < H) m = __vmaxs4(m, B[((yy * W + x) << 2) + wq]);
+            }
+            A[i] = m;
+            dst[i] = m;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- Detect head: DFL decode + class scores -----------------------------------------------------------
+struct HeadArgs {
+    const int8_t* box[3];       // (4 planes, n, H, W, 16) int8, channel = side*16 + bin
+    const int16_t* cls[3];      // (5 planes, n, H, W, 16) int16
+    const float* lut_exp;       // [2^K], index y + 2^K - 1
+    const int16_t* lut16;       // [65535], index l + 32767
+    const int* dflw;            // [16]
+    const int* anchors;         // [A][2]
+    float kd, id;
+    int n, K, A;
+    float4* dbox;               // (n, A) cx cy w h   (the first four rows of dbox_cls)
+    int* conf; int* cls_id;     // (n, A)
+    float* dbox_cls;            // optional (n, 84, A)
+};
+
+__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
+    __shared__ float lexp[512];
+    __shared__ int dflw[16];
+    const int top = (1 << a.K) - 1;
+    for (int i = threadIdx.x; i <= top; i += 128) lexp[i] = a.lut_exp[i];
+    if (threadIdx.x < 16) dflw[threadIdx.x] = a.dflw[threadIdx.x];
+    __syncthreads();
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= a.n * a.A) return;
+    const int img = idx / a.A, an = idx % a.A;
+    int lvl, hw, local;
+    if (an < 6400) { lvl = 0; hw = 80; local = an; }
+    else if (an < 8000) { lvl = 1; hw = 40; local = an - 6400; }
+    else { lvl = 2; hw = 20; local = an - 8000; }
+    const float stride = (float)(8 << lvl);
+    const size_t plane_px = (size_t)a.n * hw * hw;
+    const size_t pix = (size_t)img * hw * hw + local;
+    float dq[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        const int4 raw = __ldg((const int4*)(a.box[lvl] + ((size_t)side * plane_px + pix) * 16));
+        int b[16];
+        const int wv[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = (int)(int8_t)((wv[j >> 2] >> (8 * (j & 3))) & 0xff);
+        int mx = b[0];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) mx = max(mx, b[j]);
+        float e[16], S = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { e[j] = lexp[b[j] - mx + top]; S += e[j]; }        // exact: integers <= 16*M
+        int d = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int pj = (int)__fmul_rn(__fdiv_rn(e[j], S), 127.f);                     // (y / ax_sum * 127).to(int64)  :1205
+            d += pj * dflw[j];                                                            // self.dfl(p)  :1232
+        }
+        dq[side] = (float)requant((float)d, a.kd, a.id, 32767);                           // requantize(dfl, ..., 16)  :1236
+    }
+    const float ax = (float)a.anchors[2 * an], ay = (float)a.anchors[2 * an + 1];
+    const float x1 = ax - dq[0], y1 = ay - dq[1], x2 = ax + dq[2], y2 = ay + dq[3];       // dist2bbox :117-126
+    const float cx = __fmul_rn(__fdiv_rn(x1 + x2, 2.f), stride), cy = __fmul_rn(__fdiv_rn(y1 + y2, 2.f), stride);
+    const float w = __fmul_rn(x2 - x1, stride), h = __fmul_rn(y2 - y1, stride);
+    a.dbox[idx] = make_float4(cx, cy, w, h);
+    float* full = a.dbox_cls ? a.dbox_cls + (size_t)img * 84 * a.A + an : nullptr;
+    if (full) { full[0] = cx; full[(size_t)a.A] = cy; full[(size_t)2 * a.A] = w; full[(size_t)3 * a.A] = h; }
+    int best = -1, bj = 0;
+#pragma unroll
+    for (int pl = 0; pl < 5; ++pl) {
+        const int4* src = (const int4*)(a.cls[lvl] + ((size_t)pl * plane_px + pix) * 16);
+        const int4 r0 = __ldg(src), r1 = __ldg(src + 1);
+        const int wv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int l = (int)(int16_t)((wv[j >> 1] >> (16 * (j & 1))) & 0xffff);
+            const int sc = (int)__ldg(a.lut16 + l + 32767);                              // sigmoid_quant(cls, lookup_final) :1250
+            if (full) full[(size_t)(4 + pl * 16 + j) * a.A] = (float)sc;
+            if (sc > best) { best = sc; bj = pl * 16 + j; }                               // first maximum, like torch.max :326
+        }
+    }
+    a.conf[idx] = best;
+    a.cls_id[idx] = bj;
+}
+
+// per-anchor max / first argmax from a caller-provided (n,84,A) fp32 prediction tensor (ayq_nms entry)
+__global__ void __launch_bounds__(128) pred_to_cand_kernel(const float* __restrict__ pred, int n, int A,
+                                                           float4* dbox, int* conf, int* cls_id) {
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= n * A) return;
+    const int img = idx / A, an = idx % A;
+    const float* p = pred + (size_t)img * 84 * A + an;
+    dbox[idx] = make_float4(p[0], p[(size_t)A], p[(size_t)2 * A], p[(size_t)3 * A]);
+    float best = -1.f; int bj = 0;
+    for (int c = 0; c < 80; ++c) {
+        const float s = p[(size_t)(4 + c) * A];
+        if (s > best) { best = s; bj = c; }
+    }
+    conf[idx] = (int)best;
+    cls_id[idx] = bj;
+}
+
+// ---- q_NMS: coord_quant (:297-361) + nms_quant (:248-294) + clip_boxes (:403-423) ---------------------
+// One CTA (1024 threads) per image.  Ordering pinned to (score desc, candidate index asc) = a stable
+// descending argsort (SURVEY.md hard part 3).
+// mode 0: candidates come from the head (dbox xywh, conf, cls_id per anchor); output = detection rows.
+// mode 1: nms_quant() stand-alone on caller boxes (nb,4) xyxy (class offsets already added) and
+//         integer-valued scores; output = kept indices in selection order (all of them, <= 1000).
+#define NMS_THREADS 1024
+#define NMS_TOPK 1000
+#define NMS_MAXDET 300
+#define NMS_SORT_N 16384
+struct NmsArgs {
+    const float4* dbox; const int* conf; const int* cls_id;   // mode 0: (n, A)
+    const float* boxes; const float* scores;                  // mode 1: (A,4), (A)
+    int n, A, mode, max_keep;
+    float* dets;       // mode 0: (n, 300, 6)      mode 1: kept indices as float (max_keep)
+    int* counts;       // (n)
+};
+static constexpr size_t NMS_SMEM = (size_t)NMS_SORT_N * 4 + (size_t)NMS_TOPK * 32 * 4 + (size_t)NMS_TOPK * 5 * 4 + 64;
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* keys = (unsigned*)smem_raw;                          // [16384]
+    unsigned* mask = keys + NMS_SORT_N;                            // [1000][32]
+    float* bx = (float*)(mask + NMS_TOPK * 32);                    // [5][1000]: x1 y1 x2 y2 area (class-offset boxes)
+    int* sh = (int*)(bx + 5 * NMS_TOPK);                           // [0]=ncand [1]=nkeep
+    __shared__ int kept[NMS_TOPK];
+    const int img = blockIdx.x, tid = threadIdx.x, A = a.A;
+    const int* conf = a.mode == 0 ? a.conf + (size_t)img * A : nullptr;
+    if (tid == 0) { sh[0] = 0; sh[1] = 0; }
+    __syncthreads();
+    // candidates: conf > 8192 (:299,:302,:327); key orders by (conf desc, index asc)
+    int local = 0;
+    for (int i = tid; i < NMS_SORT_N; i += NMS_THREADS) {
+        unsigned key = 0xffffffffu;
+        if (i < A) {
+            if (a.mode == 0) {
+                const int c = conf[i];
+                if (c > 8192) { key = ((unsigned)(32767 - c) << 14) | (unsigned)i; ++local; }
+            } else {
+                const int c = (int)a.scores[i];                    // host wrapper guarantees 0 <= c <= 131071, integer
+                key = ((unsigned)(131071 - c) << 14) | (unsigned)i; ++local;
+            }
+        }
+        keys[i] = key;
+    }
+    if (local) atomicAdd(&sh[0], local);
+    __syncthreads();
+    const int ncand = sh[0];
+    if (ncand == 0) {                                              // reference: coord_quant returns None -> (None, None)
+        if (tid == 0) a.counts[img] = 0;
+        return;
+    }
+    // bitonic sort, ascending, over the smallest power of two that holds all anchors (padding keys sort last)
+    int sort_n = 1024;
+    while (sort_n < A) sort_n <<= 1;
+    for (int k = 2; k <= sort_n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < sort_n / 2; t += NMS_THREADS) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const unsigned x = keys[lo], y = keys[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    const int T = min(ncand, NMS_TOPK);                            // argsort(descending)[:1000]  :260
+    const float4* dbox = a.mode == 0 ? a.dbox + (size_t)img * A : nullptr;
+    const int* cls_id = a.mode == 0 ? a.cls_id + (size_t)img * A : nullptr;
+    for (int i = tid; i < T; i += NMS_THREADS) {
+        const int an = (int)(keys[i] & 0x3fffu);
+        float x1, y1, x2, y2;
+        if (a.mode == 0) {
+            const float4 d = dbox[an];
+            const float dw = __fdiv_rn(d.z, 2.f), dh = __fdiv_rn(d.w, 2.f);      // xywh2xyxy :129-148, .to(int) :316
+            const float off = __fmul_rn((float)cls_id[an], 7680.f);                // :340
+            x1 = truncf(d.x - dw) + off; y1 = truncf(d.y - dh) + off;              // boxes = x[:, :4] + c  :344
+            x2 = truncf(d.x + dw) + off; y2 = truncf(d.y + dh) + off;
+        } else {
+            x1 = a.boxes[4 * an]; y1 = a.boxes[4 * an + 1]; x2 = a.boxes[4 * an + 2]; y2 = a.boxes[4 * an + 3];
+        }
+        bx[i] = x1; bx[NMS_TOPK + i] = y1; bx[2 * NMS_TOPK + i] = x2; bx[3 * NMS_TOPK + i] = y2;
+        bx[4 * NMS_TOPK + i] = __fmul_rn((x2 - x1) + 412.f, (y2 - y1) + 412.f);    // areas :258
+    }
+    __syncthreads();
+    // suppression matrix: bit j of mask[i] set <=> j > i and box i removes box j  (:270-283)
+    const int nwords = (T + 31) >> 5;
+    for (int item = tid; item < T * nwords; item += NMS_THREADS) {
+        const int i = item / nwords, wq = item % nwords;
+        unsigned bits = 0;
+        if (wq * 32 + 31 > i) {
+            const float x1 = bx[i], y1 = bx[NMS_TOPK + i], x2 = bx[2 * NMS_TOPK + i], y2 = bx[3 * NMS_TOPK + i];
+            const float ar = bx[4 * NMS_TOPK + i];
+            for (int b = 0; b < 32; ++b) {
+                const int j = wq * 32 + b;
+                if (j <= i || j >= T) continue;
+                const float xx1 = fmaxf(x1, bx[j]), yy1 = fmaxf(y1, bx[NMS_TOPK + j]);
+                const float xx2 = fminf(x2, bx[2 * NMS_TOPK + j]), yy2 = fminf(y2, bx[3 * NMS_TOPK + j]);
+                const float w = fmaxf(0.f, (xx2 - xx1) + 412.f), h = fmaxf(0.f, (yy2 - yy1) + 412.f);
+                const float inter = __fmul_rn(__fmul_rn(w, h), 2.22f);
+                const float rhs = __fadd_rn(ar, bx[4 * NMS_TOPK + j]) - inter;
+                if (!(inter <= rhs)) bits |= 1u << b;
+            }
+        }
+        mask[i * 32 + wq] = bits;
+    }
+    __syncthreads();
+    if (tid < 32) {                                                // greedy scan, one warp; lane = word of the removed set
+        unsigned removed = 0;
+        int nk = 0;
+        for (int i = 0; i < T && nk < a.max_keep; ++i) {
+            const unsigned wsel = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((wsel >> (i & 31)) & 1u)) {
+                if (tid == 0) kept[nk] = i;
+                ++nk;
+                if (tid < nwords) removed |= mask[i * 32 + tid];
+            }
+        }
+        if (tid == 0) { sh[1] = nk; a.counts[img] = nk; }
+    }
+    __syncthreads();
+    const int nk = sh[1];
+    for (int r = tid; r < nk; r += NMS_THREADS) {
+        const int i = kept[r];
+        const int an = (int)(keys[i] & 0x3fffu);
+        if (a.mode != 0) { a.dets[r] = (float)an; continue; }
+        float* row = a.dets + ((size_t)img * NMS_MAXDET + r) * 6;
+        // output rows hold the un-offset boxes x[:, :4] (:351-359), then clip to [0, 640] (:403-423)
+        const float4 d = dbox[an];
+        const float dw = __fdiv_rn(d.z, 2.f), dh = __fdiv_rn(d.w, 2.f);
+        const float c[4] = {truncf(d.x - dw), truncf(d.y - dh), truncf(d.x + dw), truncf(d.y + dh)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row[q] = fminf(fmaxf(__fdiv_rn(c[q], 412.1635f), 0.f), 640.f);
+        row[4] = __fdiv_rn((float)conf[an], 32767.0f);
+        row[5] = (float)cls_id[an];
+    }
+}
+
+// ---- export a plane buffer as NCHW int32 (parity taps) ------------------------------------------------
+__global__ void export_planes_kernel(const void* __restrict__ src, int elem_bytes, int nplanes, int n, int H, int W, int* __restrict__ dst) {
+    const size_t total = (size_t)n * nplanes * 16 * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const int c = (int)((i / ((size_t)W * H)) % (nplanes * 16));
+        const int img = (int)(i / ((size_t)W * H * nplanes * 16));
+        const size_t s = (((size_t)(c >> 4) * n + img) * H * W + (size_t)y * W + x) * 16 + (c & 15);
+        dst[i] = elem_bytes == 1 ? (int)((const int8_t*)src)[s] : (int)((const int16_t*)src)[s];
+    }
+}
+
+// ---- quantised layer library on fp32-carried integer tensors (unit-level drop-ins) --------------------
+__global__ void requantize_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ k,
+                                      const float* __restrict__ inv, int per_channel, int c, int hw, size_t total, int M) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = per_channel ? (int)((i / hw) % c) : 0;
+        y[i] = (float)requant(x[i], k[ch], inv[ch], M);
+    }
+}
+__global__ void silu_f32_kernel(const float* __restrict__ acc, float* __restrict__ y, const float* __restrict__ tab,
+                                const float* __restrict__ lut, int c, int hw, size_t total, int M) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)((i / hw) % c);
+        const float a = acc[i];
+        const int r1 = rq_round(__fmul_rn(tab[ch], a), tab[c + ch], M);
+        const float pr = __fmul_rn(lut[r1 + M], a);
+        y[i] = (float)rq_round(__fmul_rn(tab[2 * c + ch], pr), tab[3 * c + ch], M);
+    }
+}
+__global__ void lut_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ lut,
+                               int key_min, int key_max, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const float r = rintf(v);
+        y[i] = (r == v && r >= (float)key_min && r <= (float)key_max) ? lut[(int)r - key_min] : 0.f;
+    }
+}
+__global__ void quant_input_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ amax,
+                                       float* __restrict__ scales, size_t per_image, int n, int M) {
+    const size_t total = per_image * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int img = (int)(i / per_image);
+        const float a = amax[img];
+        const float s = __fdiv_rn((float)M, a);
+        if (i % per_image == 0) scales[img] = s;
+        const float v = fminf(fmaxf(x[i], -a), a);
+        y[i] = a > 0.f ? rintf(__fmul_rn(v, s)) : 0.f;
+    }
+}
+
+}  // namespace ayq

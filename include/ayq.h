@@ -1,0 +1,103 @@
+/* ayq.h -- C ABI of the B200-native integer YOLOv8n + q_NMS engine (libayq.so).
+ *
+ * The reference (Alpha-Chip/Alpha-Yolo-Quant) is pure Python and has no FFI; the boundary it
+ * exposes is the set of Python names at the bottom of quantisation/stage_8_torch_full_quant.py.
+ * Each entry point below names the reference code it replaces (paths relative to
+ * /root/reference/quantisation/).  The Python shim alpha_yolo_quant_b200/ binds these with
+ * ctypes and re-exports the reference's names.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative errno-style code, ayq_last_error() gives the message of the last failure on the
+ * calling thread; image / detection buffers are caller-owned (torch allocations), the engine owns
+ * its packed weights, tables and activation workspace; all launches go to the caller's stream
+ * (a cudaStream_t passed as void*); a handle is bound to one GPU and is not thread-safe.
+ */
+#ifndef AYQ_H
+#define AYQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ayq_engine* ayq_handle;
+
+#define AYQ_MAX_DET 300          /* max_det, stage_8_torch_full_quant.py:312 */
+#define AYQ_ANCHORS 8400         /* 80*80 + 40*40 + 20*20 anchors at 640x640 */
+#define AYQ_DET_STRIDE 6         /* x1 y1 x2 y2 conf class, stage_8_torch_full_quant.py:355-359 */
+
+const char* ayq_last_error(void);
+int ayq_version(void);
+
+/* Yolov8() + load_state_dict() (stage_8_torch_full_quant.py:1278-1281) and the import-time
+ * globals all_scales / max_a_dict / lookup* (:432-436): the plan blob is produced by
+ * alpha_yolo_quant_b200.plan.compile_plan() from the same three artefacts. */
+int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_handle* out);
+int ayq_destroy(ayq_handle h);
+
+/* images processed per internal pass (activation workspace is sized for this many); default 64 */
+int ayq_set_max_batch(ayq_handle h, int max_batch);
+/* bytes of engine-owned device workspace currently allocated */
+size_t ayq_workspace_bytes(ayq_handle h);
+
+/* Yolov8.forward (stage_8_torch_full_quant.py:704-1275) for a batch: element i of the outputs
+ * equals the reference's model(img[i:i+1]).
+ *   img       device, float32 (n,3,640,640) in [0,1]            (read only)
+ *   dbox_cls  device, float32 (n,84,8400) or NULL: the tensor passed to coord_quant (:1261)
+ *   dets      device, float32 (n,300,6): rows [x1,y1,x2,y2,conf,class], first counts[i] valid
+ *   counts    device, int32 (n): 0 <=> the reference returns (None, None)                        */
+int ayq_forward(ayq_handle h, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream);
+
+/* The same call with HOST buffers (validation-driver loop, stage_8_torch.py:1004-1013): H2D of the
+ * images and D2H of the detections happen inside (pipelined against compute when the host buffers are
+ * pinned); returns after the results are in dets_host / counts_host. */
+int ayq_forward_host(ayq_handle h, const float* img_host, int n, float* dets_host, int32_t* counts_host);
+/* Same, images given as uint8 (n,3,640,640) CHW: ToTensor (u8 / 255, stage_8_torch.py:985-990) runs on the GPU. */
+int ayq_forward_host_u8(ayq_handle h, const uint8_t* img_host, int n, float* dets_host, int32_t* counts_host);
+
+/* Per-layer taps for parity tests: copies activation buffer `buf` (plan.info['bufs']) of the last pass
+ * into dst as int32 NCHW (n, 16*nplanes, H, W). */
+int ayq_export_buffer(ayq_handle h, int buf, int n, int32_t* dst, void* stream);
+int ayq_buffer_shape(ayq_handle h, int buf, int* channels, int* height, int* width);
+/* raw int32 conv accumulators (n, cout, H, W) of the last pass; only for plans compiled with taps */
+int ayq_export_acc_tap(ayq_handle h, int tap, int n, int32_t* dst, void* stream);
+/* number of kernels one internal pass launches (bench.py gpu_launches) */
+int ayq_launches_per_pass(ayq_handle h);
+/* select the convolution kernel family: 0 = CUDA-core dp4a kernel, 1 = tcgen05/TMEM kernel */
+int ayq_set_conv_impl(ayq_handle h, int impl);
+/* kernel time accounting: when enabled, every pass records CUDA events around each op;
+ * ayq_get_op_times copies per-op accumulated milliseconds and launch counts (arrays of n_ops). */
+int ayq_set_profiling(ayq_handle h, int enabled);
+int ayq_get_op_times(ayq_handle h, float* ms, int32_t* calls, int cap);
+
+/* ---- quantised layer library on fp32-carried integer tensors (unit-level drop-ins) ---- */
+
+/* requantize(), utils/rescale_coeff_torch.py:14-46: y = clamp(rsh(RN32(k[c]*x), s[c]), +-(2^(bits-1)-1)).
+ * x,y device float32 (n,c,hw); k, inv2s = 2^-s device float32 (c) or (1) when per_channel == 0. */
+int ayq_requantize_f32(const float* x, float* y, const float* k, const float* inv2s, int per_channel,
+                       int n, int c, int hw, int bits, void* stream);
+/* silu(), stage_8_torch_full_quant.py:439-452 with a precomputed coefficient table tab = float[4][c]
+ * (k1, 2^-s1, k2, 2^-s2) and the (2*M+1)-entry sigmoid LUT of create_sigmoid_lookup_table (utils/silu.py:32-50). */
+int ayq_silu_f32(const float* acc, float* y, const float* tab, const float* lut, int n, int c, int hw, int bits, void* stream);
+/* sigmoid_quant()/exponent_quant(), utils/silu_torch.py:4-18, utils/exp_torch.py:4-18:
+ * y = lut[x - key_min] if key_min <= x <= key_max and x is an integer else 0. */
+int ayq_lut_f32(const float* x, float* y, const float* lut, int key_min, int key_max, size_t count, void* stream);
+/* quant_matrix(), utils/quant_matrix_torch.py:57-70: per-image a = max|x|, y = rint(fl32(x * fl32(M/a))).
+ * amax: device float32 (n) scratch, scales: device float32 (n) out. */
+int ayq_quant_input_f32(const float* x, float* y, float* amax, float* scales, int n, size_t per_image, int bits, void* stream);
+/* save_max_a(), utils/save_a.py:11-26: out[i] = max|x[i, :]| over per_image floats (calibration taps). */
+int ayq_absmax_f32(const float* x, float* out, int n, size_t per_image, void* stream);
+/* coord_quant() + nms_quant() + scale_boxes/clip_boxes (stage_8_torch_full_quant.py:248-423) on a
+ * caller-provided prediction tensor: dbox_cls device float32 (n,84,8400). */
+int ayq_nms(ayq_handle h, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream);
+/* nms_quant(dets, scores, thresh) (stage_8_torch_full_quant.py:248-294) stand-alone: boxes device float32 (nb,4)
+ * xyxy, scores device float32 (nb) holding integers in [0, 131071], nb <= 16384.  keep: device float32 (1000)
+ * receives the kept indices in selection order (stable tie-break), count: device int32 (1). */
+int ayq_nms_boxes(const float* boxes, const float* scores, int nb, float* keep, int32_t* count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AYQ_H */

@@ -1,0 +1,260 @@
+"""GPU parity tests proper (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libayq.so via ctypes); the numpy oracle and the committed reference goldens are the checkers.
+Bit-exact: every conv accumulator, every SiLU / requantize output, decoded boxes, class scores,
+kept detections."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, yolo_int as Y
+
+pytestmark = pytest.mark.gpu
+
+REQUANT_ORDER = [('C2F_2_bottle_1', 0), ('C2F_4_bottle_1', 0), ('C2F_4_bottle_3', 0), ('C2F_6_bottle_1', 0),
+                 ('C2F_6_bottle_3', 0), ('C2F_8_bottle_1', 0), ('SPPF_conv_1', 0), ('C2F_12_bottle_1', 0),
+                 ('C2F_12_conv_1', 0), ('C2F_15_bottle_1', 0), ('C2F_12_conv_1', 1), ('C2F_18_bottle_1', 0),
+                 ('SPPF_conv_1', 1), ('C2F_21_bottle_1', 0), ('x_result_5_up_2', 0), ('x_result_6_up_2', 0),
+                 ('x_up_2', 0), ('x_result_5_down_2', 0), ('x_result_6_down_2', 0), ('x_down_2', 0)]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def _setup(golden_dir, k, taps, impl='dp4a', max_batch=64):
+    from alpha_yolo_quant_b200 import engine, loaders, plan
+    K, sd, sc, ma = loaders.load_workload_npz(os.path.join(golden_dir, f'workload_k{k}.npz'))
+    p = plan.compile_plan(sd, sc, ma, K, taps=taps)
+    e = engine.Engine(p, 0, max_batch)
+    e.set_conv_impl(impl)
+    return p, e
+
+
+def _images(seeds):
+    return torch.from_numpy(synth.to_input_array([synth.synth_image_u8(s) for s in seeds]))
+
+
+IMPLS = ['dp4a', 'tcgen05']
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('k', [8, 6, 4])
+def test_every_tensor_matches_reference_goldens(golden_dir, k, impl):
+    """Images 0..3 of the committed goldens (recorded from the unmodified reference): sha256 of all 63 conv
+    accumulators, 57 SiLU outputs, 20 requantize outputs, dbox, class scores, detections."""
+    g = np.load(os.path.join(golden_dir, f'golden_k{k}.npz'))
+    p, e = _setup(golden_dir, k, taps=True, impl=impl)
+    n = 4 if k == 8 else 2
+    x = _images(range(n)).cuda()
+    dets, counts, dbc = e.forward(x, want_dbox_cls=True)
+    torch.cuda.synchronize()
+    from alpha_yolo_quant_b200 import plan as P
+    bad = []
+    acc = [e.export_acc_tap(t, n).cpu().numpy() for t in range(p.n_acc_taps)]
+    silu_layers = [nm for nm, _ in P.LAYERS if 'silu_buf' in p.info['layers'][nm]]
+    assert len(acc) == 63 and len(silu_layers) == 57
+    silu = [e.export_buffer(p.info['layers'][nm]['silu_buf'], n).cpu().numpy() for nm in silu_layers]
+    rq = [e.export_buffer(p.info['layers'][nm]['requant_bufs'][j][0], n).cpu().numpy() for nm, j in REQUANT_ORDER]
+    dbc = dbc.cpu().numpy()
+    for i in range(n):
+        pre = f'img{i}_'
+        for t in range(63):
+            if sha(acc[t][i:i + 1]) != g[pre + 'conv_sha'][t]:
+                bad.append((i, 'conv', P.LAYERS[t][0]))
+        for t in range(57):
+            if sha(silu[t][i:i + 1]) != g[pre + 'silu_sha'][t]:
+                bad.append((i, 'silu', silu_layers[t]))
+        for t in range(20):
+            if sha(rq[t][i:i + 1]) != g[pre + 'requant_sha'][t]:
+                bad.append((i, 'requant', REQUANT_ORDER[t]))
+        if not np.array_equal(dbc[i, :4].astype(np.int32), g[pre + 'dbox']):
+            bad.append((i, 'dbox'))
+        if sha(dbc[i, 4:].astype(np.int32)) != str(g[pre + 'cls_sha']):
+            bad.append((i, 'cls'))
+        c = int(counts[i])
+        if c != g[pre + 'boxes'].shape[0]:
+            bad.append((i, 'count', c, g[pre + 'boxes'].shape[0]))
+        elif c:
+            d = dets[i, :c].cpu().numpy()
+            if not (np.array_equal(d[:, :4], g[pre + 'boxes']) and np.array_equal(d[:, 4:6], g[pre + 'classes'])):
+                bad.append((i, 'dets'))
+    assert not bad, bad[:12]
+    e.close()
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_all_golden_detections(golden_dir, impl):
+    """All 12 golden images (0, <1000 and >1000 NMS candidates) through the production plan (no taps)."""
+    g = np.load(os.path.join(golden_dir, 'golden_k8.npz'))
+    p, e = _setup(golden_dir, 8, taps=False, impl=impl)
+    n = int(g['n_images'])
+    dets, counts = e.forward(_images(range(n)).cuda())
+    seen = set()
+    for i in range(n):
+        pre = f'img{i}_'
+        c = int(counts[i])
+        ncand = int(g[pre + 'ncand'])
+        seen.add(0 if ncand == 0 else (1 if ncand < 1000 else 2))
+        assert c == g[pre + 'boxes'].shape[0], (i, c)
+        d = dets[i, :c].cpu().numpy()
+        assert np.array_equal(d[:, :4], g[pre + 'boxes']) and np.array_equal(d[:, 4:6], g[pre + 'classes']), i
+    assert seen == {0, 1, 2}
+    e.close()
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_fresh_images_match_oracle_and_batching_is_invariant(golden_dir, impl):
+    """Seeds the goldens never saw: CUDA == oracle; results do not depend on batch composition / pass size."""
+    p, e = _setup(golden_dir, 8, taps=False, impl=impl, max_batch=3)
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = Y.OracleYolov8(wl)
+    seeds = [101, 102, 103, 104, 105]
+    xs = _images(seeds)
+    ref = o.forward(xs.numpy())
+    dets, counts, dbc = e.forward(xs.cuda(), want_dbox_cls=True)       # 2 passes: 3 + 2 images (ragged)
+    assert np.array_equal(dbc[:, :4].cpu().numpy(), o.last['dbox'])
+    assert np.array_equal(dbc[:, 4:].cpu().numpy(), o.last['score'])
+    for i, (b, c) in enumerate(ref):
+        k = int(counts[i])
+        if b is None:
+            assert k == 0
+        else:
+            assert k == b.shape[0]
+            d = dets[i, :k].cpu().numpy()
+            assert np.array_equal(d[:, :4], b) and np.array_equal(d[:, 4:6], c)
+    e.set_max_batch(64)
+    d1, c1 = e.forward(xs[[3]].cuda())
+    assert int(c1[0]) == int(counts[3]) and torch.equal(d1[0, :int(c1[0])], dets[3, :int(c1[0])])
+    e.close()
+
+
+def test_host_entry_points(golden_dir):
+    """ayq_forward_host / ayq_forward_host_u8 (H2D + D2H inside, double-buffered passes) == device entry."""
+    p, e = _setup(golden_dir, 8, taps=False, max_batch=2)
+    seeds = [0, 1, 2, 5, 6]
+    u8 = torch.from_numpy(np.stack([synth.synth_image_u8(s) for s in seeds]))
+    xs = _images(seeds)
+    dets, counts = e.forward(xs.cuda())
+    dh, ch = e.forward_host(xs.pin_memory())
+    du, cu = e.forward_host(u8.pin_memory())
+    assert torch.equal(ch, counts.cpu()) and torch.equal(cu, counts.cpu())
+    for i in range(len(seeds)):
+        k = int(ch[i])
+        assert torch.equal(dh[i, :k], dets[i, :k].cpu()) and torch.equal(du[i, :k], dets[i, :k].cpu())
+    e.close()
+
+
+def test_drop_in_module(golden_dir):
+    """The reference's own driver lines (stage_8_torch_full_quant.py:1278-1294) against the shim."""
+    from alpha_yolo_quant_b200 import stage_8_torch_full_quant as S
+    g = np.load(os.path.join(golden_dir, 'golden_k8.npz'))
+    sd = S.configure(workload=os.path.join(golden_dir, 'workload_k8.npz'))
+    model = S.Yolov8()
+    model = model.to('cuda')
+    model.load_state_dict(sd)
+    model.eval()
+    for i in (0, 1, 3):
+        img = synth.to_input_tensor(synth.synth_image_u8(i))
+        with torch.no_grad():
+            boxes, classes = model(img)
+        if g[f'img{i}_boxes'].shape[0] == 0:
+            assert boxes is None and classes is None
+        else:
+            assert np.array_equal(boxes.cpu().numpy(), g[f'img{i}_boxes'])
+            assert np.array_equal(classes.cpu().numpy(), g[f'img{i}_classes'])
+    res = model.forward_batch(torch.cat([synth.to_input_tensor(synth.synth_image_u8(i)) for i in (0, 1)]))
+    assert len(res) == 2
+
+
+def test_layer_library_functions(golden_dir):
+    """requantize / silu / sigmoid_quant / exponent_quant / quant_matrix / nms_quant / coord_quant on CUDA fp32
+    tensors against the oracle restatement (same signatures as the reference)."""
+    from alpha_yolo_quant_b200 import stage_8_torch_full_quant as S
+    S.configure(workload=os.path.join(golden_dir, 'workload_k8.npz'))
+    rng = np.random.default_rng(0)
+    # requantize: scalar and per-channel, products beyond 2^31
+    x = rng.integers(-800000, 800000, size=(2, 16, 9, 7)).astype(np.float32)
+    sc = (rng.random(16).astype(np.float32) * 3000 + 40).reshape(1, 16, 1, 1)
+    q, kk, ss = S.requantize(torch.from_numpy(x).cuda(), torch.from_numpy(sc), 21.1666, 8, 'cuda')
+    qo, ko, so = Y.requantize(x.astype(np.int64), sc.reshape(-1), 21.1666, 8)
+    assert np.array_equal(q.cpu().numpy(), qo.astype(np.float32))
+    assert np.array_equal(kk.cpu().numpy().reshape(-1), ko) and np.array_equal(ss.cpu().numpy().reshape(-1), so)
+    q, _, _ = S.requantize(torch.from_numpy(x[:, :1]).cuda(), 17.25, 3.5, 8, 'cuda')
+    assert np.array_equal(q.cpu().numpy(), Y.requantize(x[:, :1].astype(np.int64), 17.25, 3.5, 8)[0].astype(np.float32))
+    # silu
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = Y.OracleYolov8(wl)
+    acc = rng.integers(-300000, 300000, size=(1, 32, 5, 5))
+    y, s_new = S.silu(torch.from_numpy(acc.astype(np.float32)).cuda(), S.all_scales['Conv_P2'], S.max_a_dict['conv_0_c2f'])
+    yo, so = o._silu(acc.astype(np.int64), 'Conv_P2', 'conv_0_c2f')
+    assert np.array_equal(y.cpu().numpy(), yo.astype(np.float32)) and s_new == so
+    # LUTs incl. keys outside the table (-> 0)
+    v = torch.tensor([-300., -127., -1., 0., 5., 127., 128., 0.5]).cuda()
+    r = S.sigmoid_quant(v, S.lookup, 'cuda').cpu().numpy()
+    assert r[0] == 0 and r[6] == 0 and r[7] == 0 and r[3] == S.lookup[0] and r[5] == S.lookup[127]
+    r = S.exponent_quant(torch.tensor([-255., -10., 0., 1.]).cuda(), S.lookup_exp, 'cuda').cpu().numpy()
+    assert r.tolist() == [S.lookup_exp[-255], S.lookup_exp[-10], S.lookup_exp[0], 0.0]
+    # quant_matrix
+    img = synth.to_input_array([synth.synth_image_u8(3), synth.synth_image_u8(1)])
+    qm, scales = S.quant_matrix(torch.from_numpy(img).cuda(), 8)
+    qo, so = Y.quant_input(img, 8)
+    assert np.array_equal(qm.cpu().numpy(), qo.astype(np.float32)) and np.array_equal(scales.cpu().numpy().reshape(-1), so)
+
+
+def test_absmax_calibration_reduction():
+    """save_max_a (utils/save_a.py:11-26): abs(t).max() per image, ragged sizes, negative extremum, empty input."""
+    import ctypes
+    from alpha_yolo_quant_b200 import engine
+    lib = engine.load_library()
+    rng = np.random.default_rng(1)
+    for per in (1, 3, 1000, 4097, 3 * 640 * 640):
+        x = (rng.standard_normal((3, per)) * 5).astype(np.float32)
+        x[1, per // 2] = -77.5
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty(3, device='cuda')
+        engine.check(lib.ayq_absmax_f32(xd.data_ptr(), out.data_ptr(), 3, per, None))
+        assert np.array_equal(out.cpu().numpy(), np.abs(x).max(1))
+    out = torch.full((2,), 5.0, device='cuda')
+    engine.check(lib.ayq_absmax_f32(xd.data_ptr(), out.data_ptr(), 2, 0, None))
+    assert out.cpu().tolist() == [0.0, 0.0]
+
+
+def test_nms_entry_points(golden_dir):
+    """ayq_nms on recorded predictions (0 / <1000 / >1000 candidates) and nms_quant stand-alone incl. ties."""
+    from alpha_yolo_quant_b200 import stage_8_torch_full_quant as S
+    g = np.load(os.path.join(golden_dir, 'golden_k8.npz'))
+    p, e = _setup(golden_dir, 8, taps=False)
+    n = int(g['n_images'])
+    pred = np.zeros((n, 84, 8400), np.float32)
+    for i in range(n):
+        pred[i, :4] = g[f'img{i}_dbox']
+        pred[i, 4 + g[f'img{i}_score_arg'].astype(np.int64), np.arange(8400)] = g[f'img{i}_score_max']
+    dets, counts = e.nms(torch.from_numpy(pred).cuda())
+    for i in range(n):
+        c = int(counts[i])
+        assert c == g[f'img{i}_boxes'].shape[0]
+        assert np.array_equal(dets[i, :c, :4].cpu().numpy(), g[f'img{i}_boxes'])
+    # nms_quant: random boxes with many tied scores vs the oracle's greedy loop
+    rng = np.random.default_rng(2)
+    nb = 1500
+    xy = rng.integers(0, 200000, size=(nb, 2)).astype(np.float32)
+    wh = rng.integers(2000, 60000, size=(nb, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = rng.integers(8193, 8193 + 40, size=nb).astype(np.float32)
+    keep = S.nms_quant(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.45).cpu().numpy().astype(np.int64)
+    order = np.argsort(-scores, kind='stable')[:1000]
+    x1, y1, x2, y2 = boxes.T
+    F = np.float32
+    areas = ((x2 - x1 + F(412)) * (y2 - y1 + F(412))).astype(F)
+    exp = []
+    while order.size:
+        i = order[0]; exp.append(i); rest = order[1:]
+        w = np.maximum(F(0), np.minimum(x2[i], x2[rest]) - np.maximum(x1[i], x1[rest]) + F(412))
+        h = np.maximum(F(0), np.minimum(y2[i], y2[rest]) - np.maximum(y1[i], y1[rest]) + F(412))
+        inter = ((w * h).astype(F) * F(2.22)).astype(F)
+        order = rest[inter <= ((areas[i] + areas[rest]).astype(F) - inter).astype(F)]
+    assert keep.tolist() == [int(v) for v in exp]
+    e.close()
