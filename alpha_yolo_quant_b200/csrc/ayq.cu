@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,7 @@ struct ayq_engine {
     std::vector<int*> acc_taps;            // per tap device buffers (cap images)
     std::vector<size_t> acc_tap_elems;     // per image
     int conv_impl = 0;
+    bool debug_sync = false;
     int last_n = 0;
     // host-pipeline resources
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -175,9 +177,10 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
         delete e;
         return fail(-12, "ayq_create: cannot upload %llu bytes of plan data", (unsigned long long)h.data_bytes);
     }
-    cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM);
+    CK(cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
+    e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     tc_init(e->tc);
     e->op_ms.assign(h.n_ops + 1, 0.f);
     e->op_calls.assign(h.n_ops + 1, 0);
@@ -273,7 +276,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     }
     const size_t npix = (size_t)n * a.Hout * a.Wout;
     const unsigned gx = (unsigned)((npix + 127) / 128);
-    const size_t lut_bytes = (size_t)(2 * a.M + 1) * 4;
+    const size_t lut_bytes = a.epi == 0 ? (size_t)(2 * a.M + 1) * 4 : 0;   // the sigmoid table is only read by the SiLU epilogue
     if (a.cout % 32 == 0) {
         conv_dp4a_kernel<32><<<dim3(gx, a.cout / 32), 128, (size_t)a.nkc * 32 * 16 + lut_bytes, st>>>(a);
     } else {
@@ -294,6 +297,11 @@ static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, flo
     CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
     absmax_kernel<<<dim3(64, n), 256, 0, st>>>(img, amax, (size_t)3 * H * W);
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
+    if (e->debug_sync) {
+        cudaError_t de = cudaStreamSynchronize(st);
+        if (de == cudaSuccess) de = cudaGetLastError();
+        if (de != cudaSuccess) return fail(-5, "absmax failed: %s", cudaGetErrorString(de));
+    }
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const int32_t* f = e->ops[i].f;
         switch (f[0]) {
@@ -352,6 +360,11 @@ static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, flo
             return fail(-22, "plan op %zu has unknown kind %d", i, f[0]);
         }
         if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
+        if (e->debug_sync) {
+            cudaError_t de = cudaStreamSynchronize(st);
+            if (de == cudaSuccess) de = cudaGetLastError();
+            if (de != cudaSuccess) return fail(-5, "op %zu (kind %d) failed: %s", i, f[0], cudaGetErrorString(de));
+        }
     }
     CK(cudaGetLastError());
     if (prof) {
