@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(128) conv_p1_kernel(const P1Args a) {
     const int ox = (int)(p % a.Wout);
     const int oy = (int)((p / a.Wout) % a.Hout);
     const int img = (int)(p / ((size_t)a.Wout * a.Hout));
-    // quant_matrix: a = max|x|, s = fl32(M / a), q = rint(fl32(clip(x) * s))   (utils/quant_matrix_torch.py:57-70)
+    // quant_matrix: a = max|x|, s = scale(a, k) = M / a evaluated by torch as reciprocal(a) * M (Tensor.__rtruediv__),
+    // q = rint(fl32(clip(x) * s))   (utils/quant_matrix_torch.py:57-70, utils/scale.py:4-5)
     const float amax = a.amax[img];
-    const float s = __fdiv_rn((float)a.M, amax);
+    const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);
     int q[28];
 #pragma unroll
     for (int i = 0; i < 28; ++i) q[i] = 0;
@@ -572,7 +573,7 @@ __global__ void quant_input_f32_kernel(const float* __restrict__ x, float* __res
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int img = (int)(i / per_image);
         const float a = amax[img];
-        const float s = __fdiv_rn((float)M, a);
+        const float s = __fmul_rn(__frcp_rn(a), (float)M);      // M / tensor == reciprocal(tensor) * M in torch
         if (i % per_image == 0) scales[img] = s;
         const float v = fminf(fmaxf(x[i], -a), a);
         y[i] = a > 0.f ? rintf(__fmul_rn(v, s)) : 0.f;

@@ -163,7 +163,9 @@ def upsample2(x):
 
 
 def quant_input(x, k):
-    """utils/quant_matrix_torch.py:57-70: per image a = max|x|, scale = fl32(M/a), q = rint(fl32(x*scale)).
+    """utils/quant_matrix_torch.py:57-70: per image a = max|x| (a 0-dim fp32 tensor), scale = scale(a, k) = M / a,
+    q = rint(fl32(x*scale)).  `python_int / tensor` is Tensor.__rtruediv__ = reciprocal(a) * M in torch, i.e.
+    fl32(fl32(1/a) * M), NOT fl32(M/a): the two differ in the last ulp for some a (golden image 8, a = 244/255).
     Returns int64 (N,3,H,W) and the per-image fp32 scales."""
     x = np.asarray(x, F32)
     out = np.empty(x.shape, np.int64)
@@ -172,7 +174,7 @@ def quant_input(x, k):
     for i in range(x.shape[0]):
         a = np.abs(x[i]).max()
         with np.errstate(all='ignore'):
-            s = F32(m) / F32(a)
+            s = F32(F32(1) / F32(a)) * F32(m)
             out[i] = np.rint((np.clip(x[i], -a, a) * s).astype(F32)).astype(np.int64)
         scales[i] = s
     return out, scales
