@@ -55,7 +55,7 @@ struct ayq_engine {
     bool debug_sync = false;
     int last_n = 0;
     // host-pipeline resources
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
     float* d_img[2] = {nullptr, nullptr};
     uint8_t* d_img_u8[2] = {nullptr, nullptr};
     float* d_dets[2] = {nullptr, nullptr};
@@ -204,6 +204,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
     }
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
     return 0;
@@ -416,6 +417,7 @@ static int ensure_host_pipeline(ayq_engine* e, int m, bool u8) {
     if (!e->s_copy) {
         CK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
@@ -456,26 +458,24 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     int slot = 0, pass = 0;
     for (int i0 = 0; i0 < n; i0 += mb, ++pass, slot ^= 1) {
         const int m = (n - i0) < mb ? (n - i0) : mb;
-        if (pass >= 2) {                       // slot reuse: its previous results must have left the device
-            CK(cudaStreamWaitEvent(e->s_copy, e->ev_d2h[slot], 0));
-            CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));
-        }
+        // three streams: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i
+        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));   // d_img[slot] still being read
         if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
         else CK(cudaMemcpyAsync(e->d_img[slot], (const float*)img_host + (size_t)i0 * img_elems, img_elems * m * sizeof(float), cudaMemcpyHostToDevice, e->s_copy));
         CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
         CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
-        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));   // d_dets[slot] still draining
+        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));    // d_dets[slot] still draining
         if (u8) u8_to_f32_kernel<<<1184, 256, 0, e->s_comp>>>(e->d_img_u8[slot], e->d_img[slot], img_elems * m);
         rc = run_pass(e, e->d_img[slot], m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
         if (rc) return rc;
         CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
-        // D2H on the copy stream keeps the compute stream free for the next pass
-        CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));
+        CK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[slot], 0));
         CK(cudaMemcpyAsync(dets_host + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, e->d_dets[slot],
-                           (size_t)m * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, e->s_copy));
-        CK(cudaMemcpyAsync(counts_host + i0, e->d_counts[slot], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, e->s_copy));
-        CK(cudaEventRecord(e->ev_d2h[slot], e->s_copy));
+                           (size_t)m * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(cudaMemcpyAsync(counts_host + i0, e->d_counts[slot], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
     }
+    CK(cudaStreamSynchronize(e->s_d2h));
     CK(cudaStreamSynchronize(e->s_copy));
     CK(cudaStreamSynchronize(e->s_comp));
     return 0;

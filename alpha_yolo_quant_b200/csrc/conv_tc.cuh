@@ -1,16 +1,18 @@
-// conv_tc.cuh -- tcgen05 / TMEM implicit-GEMM quantised convolution for sm_100a.
+// conv_tc.cuh -- tcgen05 / TMEM implicit-GEMM quantised convolution for sm_100a (persistent, warp-specialised).
 //
 // GEMM view of one conv: D[M = 128 output pixels, N = cout] (int32, TMEM) += A[M, K] * B[N, K]^T with
 // K = 16-channel chunks x taps (the plan's K-chunk list, which also encodes concat and residual adds).
 //   A  (activations)  gathered from the 16-channel plane buffers by 128 producer threads with 16-byte
 //      cp.async (zero fill = conv padding): one pixel's 16 channels = one 16-byte row of a K-major core matrix.
 //   B  (weights)      packed by plan.py as [K-chunk][cout][16] int8, which IS the canonical no-swizzle K-major
-//      layout (8 rows x 16 bytes per core matrix), so a stage is ONE bulk-TMA copy (cp.async.bulk -> UBLKCP).
-//   D  accumulators in TMEM, read back with tcgen05.ld 32x32b.x16: thread = output pixel, 16 registers =
-//      16 consecutive output channels = exactly one 16-byte plane row after the fixed-point epilogue.
-// Warp roles: warps 0-3 producers then epilogue, warp 4 = MMA issuer (one thread) + TMEM allocator,
-// warp 5 = weight loader (one thread).  smem ring of NS stages, each KS K-chunks (KS*16 of K) deep.
-// One tile per CTA; several CTAs per SM overlap one tile's epilogue with the next tile's loads and MMAs.
+//      layout (8 rows x 16 bytes per core matrix): bulk-TMA copies (cp.async.bulk -> UBLKCP), either once per CTA
+//      (weights resident in smem) or one copy per pipeline stage.
+//   D  two accumulators in TMEM (tile parity), read back with tcgen05.ld 32x32b.x16: thread = output pixel,
+//      16 registers = 16 consecutive output channels = exactly one 16-byte plane row after the epilogue.
+// A tile is a box of bw x bh x bn = 128 output pixels (x, y, image).  CTAs are persistent: tile = blockIdx.x +
+// i * gridDim.x.  Warp roles: warps 0-3 producers, warps 4-7 / 8-11 epilogue of even / odd tiles (so the epilogue of
+// tile i overlaps the loads and MMAs of tile i+1), warp 12 = MMA issuer (one thread) + TMEM allocator, warp 13 =
+// weight loader (one thread).  smem ring of NS stages, each KS K-chunks (KS*16 of K) deep, runs across tiles.
 #pragma once
 #include "kernels.cuh"
 
@@ -39,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
@@ -96,39 +98,150 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* r) {
 
 struct TcParams {
     int KS;            // K chunks per stage (even)
-    int NS;            // stages in the ring
-    int nst;           // number of stages to run = ceil(nkc_pad / KS)
+    int NS;            // stages in the A ring
+    int nst;           // stages per tile = ceil(nkc_pad / KS)
     int nkc_pad;       // nkc rounded up to even
-    int tmem_cols;     // power of two >= max(32, cout)
+    int tmem_cols;     // power of two >= max(32, 2 * cout)
+    int resident_b;    // 1: all weights stay in smem for the life of the CTA
+    int bw_log, bh_log;            // tile box: 2^bw_log x 2^bh_log x (128 >> (bw_log + bh_log)) pixels (x, y, image)
+    int tiles_x, tiles_y, ntiles;
 };
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_NS = 4;
-constexpr int TC_LAG = 2;      // producer stages in flight before the oldest is published (< NS)
+constexpr int TC_PRODUCERS = 128;
+constexpr int TC_THREADS = 448;        // 4 producer + 8 epilogue + MMA + loader warps
+constexpr int TC_MAX_NS = 6;
+constexpr int TC_LAG = 2;              // producer stages in flight before the oldest is published (< NS)
 
-// dynamic smem: [A ring NS*KS*2048][B ring NS*KS*cout*16][kc table nkc*24][lut 2M+1 floats]
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, const TcParams tp) {
+struct ChunkRec { long long off; int tap; int pad_; };     // byte offset incl. plane and tap shift; tap bit index
+
+struct TileCoord { int img0, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(int t, const TcParams& tp) {
+    TileCoord c;
+    const int tx = t % tp.tiles_x;
+    const int r = t / tp.tiles_x;
+    c.x0 = tx << tp.bw_log;
+    c.y0 = (r % tp.tiles_y) << tp.bh_log;
+    c.img0 = (r / tp.tiles_y) << (7 - tp.bw_log - tp.bh_log);
+    return c;
+}
+
+// fixed-point epilogue for 16 consecutive channels of one pixel, per-channel tables in shared memory
+__device__ __forceinline__ void epilogue16_s(const ConvArgs& a, int* acc, int c0, int img, int oy, int ox,
+                                             const float* __restrict__ tab_s, const int* __restrict__ bias_s,
+                                             const float* __restrict__ lut_s) {
+    const int M = a.M, N = a.cout;
+    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
+    const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int4 b = *(const int4*)(bias_s + c0 + 4 * q);
+        acc[4 * q] += b.x; acc[4 * q + 1] += b.y; acc[4 * q + 2] += b.z; acc[4 * q + 3] += b.w;
+    }
+    if (a.acc_tap) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            a.acc_tap[(((size_t)img * N + c0 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
+    }
+    if (a.epi == 0) {                 // EPI_SILU
+        int r[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 k1 = *(const float4*)(tab_s + c0 + 4 * q), i1 = *(const float4*)(tab_s + N + c0 + 4 * q);
+            const float4 k2 = *(const float4*)(tab_s + 2 * N + c0 + 4 * q), i2 = *(const float4*)(tab_s + 3 * N + c0 + 4 * q);
+            r[4 * q] = silu_q(acc[4 * q], k1.x, i1.x, k2.x, i2.x, lut_s, M);
+            r[4 * q + 1] = silu_q(acc[4 * q + 1], k1.y, i1.y, k2.y, i2.y, lut_s, M);
+            r[4 * q + 2] = silu_q(acc[4 * q + 2], k1.z, i1.z, k2.z, i2.z, lut_s, M);
+            r[4 * q + 3] = silu_q(acc[4 * q + 3], k1.w, i1.w, k2.w, i2.w, lut_s, M);
+        }
+        for (int o = 0; o < a.nout; ++o) {
+            const OutSpec& os = a.out[o];
+            uint32_t wd[4];
+            if (os.mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    wd[j] = pack4(requant((float)r[4 * j], os.k, os.inv, M), requant((float)r[4 * j + 1], os.k, os.inv, M),
+                                  requant((float)r[4 * j + 2], os.k, os.inv, M), requant((float)r[4 * j + 3], os.k, os.inv, M));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wd[j] = pack4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+            const uint4 v = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            int8_t* base = (int8_t*)os.base;
+            if (!os.up) {
+                *(uint4*)(base + ((size_t)(c0 >> 4) * npix + pix) * 16) = v;
+            } else {             // nn.Upsample(None, 2, 'nearest') then requantize (:900-903): 2x2 replicate
+                const int W2 = a.Wout * 2;
+                const size_t p00 = ((size_t)img * a.Hout * 2 + 2 * oy) * W2 + 2 * ox;
+                int8_t* pl = base + (size_t)(c0 >> 4) * npix * 64;
+                *(uint4*)(pl + p00 * 16) = v;
+                *(uint4*)(pl + (p00 + 1) * 16) = v;
+                *(uint4*)(pl + (p00 + W2) * 16) = v;
+                *(uint4*)(pl + (p00 + W2 + 1) * 16) = v;
+            }
+        }
+    } else if (a.epi == 1) {          // EPI_REQUANT8
+        uint32_t wd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 k = *(const float4*)(tab_s + c0 + 4 * q), iv = *(const float4*)(tab_s + N + c0 + 4 * q);
+            wd[q] = pack4(requant(__int2float_rn(acc[4 * q]), k.x, iv.x, M), requant(__int2float_rn(acc[4 * q + 1]), k.y, iv.y, M),
+                          requant(__int2float_rn(acc[4 * q + 2]), k.z, iv.z, M), requant(__int2float_rn(acc[4 * q + 3]), k.w, iv.w, M));
+        }
+        *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    } else {                          // EPI_REQUANT16
+        uint32_t wd[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 k = *(const float4*)(tab_s + c0 + 4 * q), iv = *(const float4*)(tab_s + N + c0 + 4 * q);
+            const int q0 = requant(__int2float_rn(acc[4 * q]), k.x, iv.x, M), q1 = requant(__int2float_rn(acc[4 * q + 1]), k.y, iv.y, M);
+            const int q2 = requant(__int2float_rn(acc[4 * q + 2]), k.z, iv.z, M), q3 = requant(__int2float_rn(acc[4 * q + 3]), k.w, iv.w, M);
+            wd[2 * q] = (uint32_t)(q0 & 0xffff) | ((uint32_t)(q1 & 0xffff) << 16);
+            wd[2 * q + 1] = (uint32_t)(q2 & 0xffff) | ((uint32_t)(q3 & 0xffff) << 16);
+        }
+        uint4* dst = (uint4*)((int16_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16);
+        dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+    }
+}
+
+// dynamic smem: [A ring NS*KS*2048][B: resident nkc_pad*N*16 | ring NS*KS*N*16][chunk table nkc*16][tab 4N f32][bias N i32][lut]
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcParams tp) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 1];   // full[NS], empty[NS], tmem_full
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 5];   // full[NS], empty[NS], tfull[2], tempty[2], wfull
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.cout, KS = tp.KS, NS = tp.NS, nst = tp.nst;
     const uint32_t a_stage_bytes = (uint32_t)KS * 2048u, b_stage_bytes = (uint32_t)KS * N * 16u;
     unsigned char* sA = smem;
     unsigned char* sB = smem + (size_t)NS * a_stage_bytes;
-    KChunk* skc = (KChunk*)(sB + (size_t)NS * b_stage_bytes);
-    float* lut_s = (float*)(skc + a.nkc);
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]), tfull = smem_u32(&bars[2 * TC_MAX_NS]);
+    const size_t b_bytes = tp.resident_b ? (size_t)tp.nkc_pad * N * 16 : (size_t)NS * b_stage_bytes;
+    ChunkRec* skc = (ChunkRec*)(sB + b_bytes);
+    float* tab_s = (float*)(skc + a.nkc);
+    int* bias_s = (int*)(tab_s + 4 * N);
+    float* lut_s = (float*)(bias_s + N);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
 
-    for (int i = tid; i < a.nkc; i += TC_THREADS) skc[i] = a.kc[i];
+    for (int i = tid; i < a.nkc; i += TC_THREADS) {
+        const KChunk k = a.kc[i];
+        ChunkRec r;
+        r.off = k.off + (long long)k.plane * (long long)a.in_plane_bytes + ((long long)k.dy * a.Win + k.dx) * 16;
+        r.tap = (k.dy + 1) * 3 + (k.dx + 1);          // 1x1 convs: dy = dx = 0 -> tap 4 (centre, always inside)
+        r.pad_ = 0;
+        skc[i] = r;
+    }
+    for (int i = tid; i < 4 * N; i += TC_THREADS) tab_s[i] = a.tab[i];
+    for (int i = tid; i < N; i += TC_THREADS) bias_s[i] = a.bias[i];
     if (a.epi == 0)
         for (int i = tid; i < 2 * a.M + 1; i += TC_THREADS) lut_s[i] = a.lut[i];
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 128 + 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        const uint32_t full_count = TC_PRODUCERS + (tp.resident_b ? 0 : 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)tp.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -138,92 +251,128 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, c
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < 4) {
-        // ===== producers: im2col gather of this thread's output pixel, then epilogue of the same pixel =====
-        const size_t npix = (size_t)a.n * a.Hout * a.Wout;
-        const size_t p = (size_t)blockIdx.x * 128 + tid;
-        const bool valid = p < npix;
-        const int ox = valid ? (int)(p % a.Wout) : 0;
-        const int oy = valid ? (int)((p / a.Wout) % a.Hout) : 0;
-        const int img = valid ? (int)(p / ((size_t)a.Wout * a.Hout)) : 0;
-        const int iy0 = oy * a.stride, ix0 = ox * a.stride;
-        const int8_t* img_base = a.ws + (size_t)img * a.Hin * a.Win * 16;
-        for (int st = 0; st < nst; ++st) {
-            const int slot = st % NS;
-            if (st >= NS) mbar_wait(empty0 + 8 * slot, ((st / NS) - 1) & 1);
-            const uint32_t dst0 = smem_u32(sA) + slot * a_stage_bytes + tid * 16;
-            const int kc0 = st * KS;
-            for (int c = 0; c < KS; ++c) {
-                const int kc = kc0 + c;
-                if (kc >= a.nkc) break;                       // odd tail chunk: its weights are zero
-                const KChunk k = skc[kc];
-                const int iy = iy0 + k.dy, ix = ix0 + k.dx;
-                const bool ok = valid && (unsigned)iy < (unsigned)a.Hin && (unsigned)ix < (unsigned)a.Win;
-                const int8_t* src = img_base + k.off + (size_t)k.plane * a.in_plane_bytes + ((size_t)(ok ? iy : 0) * a.Win + (ok ? ix : 0)) * 16;
-                cp_async16(dst0 + c * 2048, src, ok ? 16u : 0u);
-            }
-            cp_async_commit();
-            if (st >= TC_LAG) {
-                cp_async_wait<TC_LAG>();
-                fence_proxy_async();
-                mbar_arrive(full0 + 8 * ((st - TC_LAG) % NS));
+        // ===== producers: im2col gather, one output pixel (GEMM row) per thread =====
+        const int dx = tid & ((1 << tp.bw_log) - 1), dy = (tid >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = tid >> (tp.bw_log + tp.bh_log);
+        const uint32_t dst_row = smem_u32(sA) + tid * 16;
+        int g = 0;                                               // global stage counter (runs across tiles)
+        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+            const TileCoord tc0 = tile_coord(t, tp);
+            const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
+            const bool valid = img < a.n;                        // boxes tile W and H exactly; only the image dim can overhang
+            const int iy0 = oy * a.stride, ix0 = ox * a.stride;
+            unsigned tapmask = 0;
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx)
+                    if (valid && (unsigned)(iy0 + ty - 1) < (unsigned)a.Hin && (unsigned)(ix0 + tx - 1) < (unsigned)a.Win) tapmask |= 1u << (ty * 3 + tx);
+            const int8_t* base = a.ws + (((size_t)(valid ? img : 0) * a.Hin + iy0) * a.Win + ix0) * 16;
+            for (int st = 0; st < nst; ++st, ++g) {
+                const int slot = g % NS;
+                if (g >= NS) mbar_wait(empty0 + 8 * slot, ((g / NS) - 1) & 1);
+                const uint32_t dst0 = dst_row + slot * a_stage_bytes;
+                const int kc0 = st * KS;
+                const int kend = min(KS, a.nkc - kc0);           // an odd tail chunk has zero weights: skip it
+                for (int c = 0; c < kend; ++c) {
+                    const ChunkRec k = skc[kc0 + c];
+                    const bool ok = (tapmask >> k.tap) & 1u;
+                    cp_async16(dst0 + c * 2048, ok ? base + k.off : a.ws, ok ? 16u : 0u);
+                }
+                cp_async_commit();
+                if (g >= TC_LAG) {
+                    cp_async_wait<TC_LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(full0 + 8 * ((g - TC_LAG) % NS));
+                }
             }
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        for (int st = (nst > TC_LAG ? nst - TC_LAG : 0); st < nst; ++st) mbar_arrive(full0 + 8 * (st % NS));
-
+        for (int s = (g > TC_LAG ? g - TC_LAG : 0); s < g; ++s) mbar_arrive(full0 + 8 * (s % NS));
+    } else if (warp < 12) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int g = 0; g < N / 16; ++g) {
-            int acc[16];
-            tmem_ld16(lane_base + (uint32_t)(g * 16), acc);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += __ldg(a.bias + g * 16 + j);
-                epilogue16(a, acc, g * 16, img, oy, ox, lut_s);
+        const int grp = (warp - 4) >> 2;                         // tile parity this group drains
+        const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
+        const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * N);
+        int it = 0;
+        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, ++it) {
+            if ((it & 1) != grp) continue;
+            const TileCoord tc0 = tile_coord(t, tp);
+            const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
+            const bool valid = img < a.n;
+            mbar_wait(tfull0 + 8 * grp, (it >> 1) & 1);
+            tc_fence_after();
+            for (int gch = 0; gch < N / 16; ++gch) {
+                int acc[16];
+                tmem_ld16(lane_base + (uint32_t)(gch * 16), acc);
+                if (gch == N / 16 - 1) {                         // accumulator fully read: hand the buffer back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tempty0 + 8 * grp);
+                }
+                if (valid) epilogue16_s(a, acc, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
             }
         }
-        tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == 12) {
         // ===== MMA issuer =====
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             const uint32_t idesc = make_idesc_i8(N);
-            uint32_t accum = 0;
-            for (int st = 0; st < nst; ++st) {
-                const int slot = st % NS;
-                mbar_wait(full0 + 8 * slot, (st / NS) & 1);
+            if (tp.resident_b) mbar_wait(wfull, 0);
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, ++it) {
+                const int b = it & 1;
+                mbar_wait(tempty0 + 8 * b, ((it >> 1) & 1) ^ 1);   // fresh barrier: parity 1 passes immediately
                 tc_fence_after();
-                const uint32_t abase = smem_u32(sA) + slot * a_stage_bytes, bbase = smem_u32(sB) + slot * b_stage_bytes;
-                const int pairs = min(KS, tp.nkc_pad - st * KS) / 2;
-                for (int j = 0; j < pairs; ++j) {
-                    const uint64_t ad = make_desc(abase + j * 4096, 2048, 128);
-                    const uint64_t bd = make_desc(bbase + j * 2 * N * 16, N * 16, 128);
-                    mma_i8(tmem_base, ad, bd, idesc, accum);
-                    accum = 1;
+                const uint32_t dcol = tmem_base + (uint32_t)(b * N);
+                uint32_t accum = 0;
+                for (int st = 0; st < nst; ++st, ++g) {
+                    const int slot = g % NS;
+                    mbar_wait(full0 + 8 * slot, (g / NS) & 1);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA) + slot * a_stage_bytes;
+                    const uint32_t bbase = smem_u32(sB) + (tp.resident_b ? (uint32_t)st : (uint32_t)slot) * b_stage_bytes;
+                    const int pairs = min(KS, tp.nkc_pad - st * KS) / 2;
+                    for (int j = 0; j < pairs; ++j) {
+                        const uint64_t ad = make_desc(abase + j * 4096, 2048, 128);
+                        const uint64_t bd = make_desc(bbase + j * 2 * N * 16, N * 16, 128);
+                        mma_i8(dcol, ad, bd, idesc, accum);
+                        accum = 1;
+                    }
+                    mma_commit(empty0 + 8 * slot);            // frees the smem slot when these MMAs retire
                 }
-                mma_commit(empty0 + 8 * slot);            // frees the smem slot when these MMAs retire
+                mma_commit(tfull0 + 8 * b);                    // accumulator complete -> epilogue group b
             }
-            mma_commit(tfull);                             // accumulator complete -> epilogue
         }
         __syncwarp();
     } else {
-        // ===== weight loader: one bulk-TMA copy per stage =====
-        if ((tid & 31) == 0) {
-            for (int st = 0; st < nst; ++st) {
-                const int slot = st % NS;
-                if (st >= NS) mbar_wait(empty0 + 8 * slot, ((st / NS) - 1) & 1);
-                const int chunks = min(KS, tp.nkc_pad - st * KS);
-                const uint32_t bytes = (uint32_t)chunks * N * 16u;
-                mbar_arrive_expect_tx(full0 + 8 * slot, bytes);
-                bulk_g2s(smem_u32(sB) + slot * b_stage_bytes, a.w + (size_t)st * KS * N * 16, bytes, full0 + 8 * slot);
+        // ===== weight loader (bulk TMA) =====
+        if (lane == 0) {
+            if (tp.resident_b) {
+                const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
+                mbar_arrive_expect_tx(wfull, total);
+                for (uint32_t o = 0; o < total; o += 32768u) {
+                    const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
+                    bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
+                }
+            } else {
+                int g = 0;
+                for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+                    for (int st = 0; st < nst; ++st, ++g) {
+                        const int slot = g % NS;
+                        if (g >= NS) mbar_wait(empty0 + 8 * slot, ((g / NS) - 1) & 1);
+                        const int chunks = min(KS, tp.nkc_pad - st * KS);
+                        const uint32_t bytes = (uint32_t)chunks * N * 16u;
+                        mbar_arrive_expect_tx(full0 + 8 * slot, bytes);
+                        bulk_g2s(smem_u32(sB) + slot * b_stage_bytes, a.w + (size_t)st * KS * N * 16, bytes, full0 + 8 * slot);
+                    }
+                }
             }
         }
         __syncwarp();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 12) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tp.tmem_cols) : "memory");
     }
@@ -232,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, c
 }  // namespace tc
 
 static inline void tc_init(TcState& s) {
-    cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -246,19 +395,34 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /
     const int N = a.cout;
     if (N % 16 != 0 || N < 16 || N > 256) return 1;
     tc::TcParams tp;
+    // tile box: widest power-of-two row segment that divides Wout, then rows, then images
+    int bw_log = 4;
+    while (bw_log > 0 && (a.Wout % (1 << bw_log))) --bw_log;
+    int bh_log = 7 - bw_log;
+    while (bh_log > 0 && (a.Hout % (1 << bh_log))) --bh_log;
+    tp.bw_log = bw_log; tp.bh_log = bh_log;
+    const int bn = 128 >> (bw_log + bh_log);
+    tp.tiles_x = a.Wout >> bw_log;
+    tp.tiles_y = a.Hout >> bh_log;
+    tp.ntiles = tp.tiles_x * tp.tiles_y * ((a.n + bn - 1) / bn);
     tp.nkc_pad = (a.nkc + 1) & ~1;
     tp.KS = tp.nkc_pad < 8 ? tp.nkc_pad : 8;
     tp.nst = (tp.nkc_pad + tp.KS - 1) / tp.KS;
-    tp.NS = tp.nst < 3 ? tp.nst : 3;
-    if (tp.NS <= tc::TC_LAG && tp.nst > tp.NS) tp.NS = tc::TC_LAG + 1;
     int cols = 32;
-    while (cols < N) cols <<= 1;
+    while (cols < 2 * N) cols <<= 1;
     tp.tmem_cols = cols;
     const size_t lut_bytes = a.epi == 0 ? (size_t)(2 * a.M + 1) * 4 : 0;
-    const size_t smem = (size_t)tp.NS * tp.KS * 2048 + (size_t)tp.NS * tp.KS * N * 16 + (size_t)a.nkc * sizeof(KChunk) + lut_bytes + 16;
-    if (smem > 220 * 1024) return 1;
-    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
-    const unsigned grid = (unsigned)((npix + 127) / 128);
+    const size_t fixed = (size_t)a.nkc * sizeof(tc::ChunkRec) + (size_t)N * 20 + lut_bytes + 64;
+    const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
+    const size_t budget = 200 * 1024;
+    tp.resident_b = w_bytes <= 96 * 1024 ? 1 : 0;
+    const size_t a_stage = (size_t)tp.KS * 2048, b_stage = (size_t)tp.KS * N * 16;
+    int ns = 4;
+    while (ns > 3 && fixed + (tp.resident_b ? w_bytes + ns * a_stage : ns * (a_stage + b_stage)) > budget) --ns;
+    tp.NS = ns;
+    const size_t smem = fixed + (tp.resident_b ? w_bytes + ns * a_stage : ns * (a_stage + b_stage));
+    if (smem > 224 * 1024) return 1;
+    unsigned grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     tc::conv_tc_kernel<<<grid, tc::TC_THREADS, smem, st>>>(a, tp);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }

@@ -419,31 +419,44 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     const int* conf = a.mode == 0 ? a.conf + (size_t)img * A : nullptr;
     if (tid == 0) { sh[0] = 0; sh[1] = 0; }
     __syncthreads();
-    // candidates: conf > 8192 (:299,:302,:327); key orders by (conf desc, index asc)
-    int local = 0;
-    for (int i = tid; i < NMS_SORT_N; i += NMS_THREADS) {
-        unsigned key = 0xffffffffu;
+    // candidates: conf > 8192 (:299,:302,:327); key orders by (conf desc, index asc).  Keys are appended in any
+    // order (the index inside the key makes the order total), then sorted.
+    for (int i0 = 0; i0 < A; i0 += NMS_THREADS) {                  // warp-uniform trip count
+        const int i = i0 + tid;
+        unsigned key = 0;
+        bool cand = false;
         if (i < A) {
             if (a.mode == 0) {
                 const int c = conf[i];
-                if (c > 8192) { key = ((unsigned)(32767 - c) << 14) | (unsigned)i; ++local; }
+                cand = c > 8192;
+                key = ((unsigned)(32767 - c) << 14) | (unsigned)i;
             } else {
                 const int c = (int)a.scores[i];                    // host wrapper guarantees 0 <= c <= 131071, integer
-                key = ((unsigned)(131071 - c) << 14) | (unsigned)i; ++local;
+                cand = true;
+                key = ((unsigned)(131071 - c) << 14) | (unsigned)i;
             }
         }
-        keys[i] = key;
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+            const int lane = tid & 31;
+            const int leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sh[0], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cand) keys[base + __popc(bal & ((1u << lane) - 1))] = key;
+        }
     }
-    if (local) atomicAdd(&sh[0], local);
     __syncthreads();
     const int ncand = sh[0];
     if (ncand == 0) {                                              // reference: coord_quant returns None -> (None, None)
         if (tid == 0) a.counts[img] = 0;
         return;
     }
-    // bitonic sort, ascending, over the smallest power of two that holds all anchors (padding keys sort last)
-    int sort_n = 1024;
-    while (sort_n < A) sort_n <<= 1;
+    // bitonic sort, ascending, over the smallest power of two that holds all candidates (padding keys sort last)
+    int sort_n = 64;
+    while (sort_n < ncand) sort_n <<= 1;
+    for (int i = ncand + tid; i < sort_n; i += NMS_THREADS) keys[i] = 0xffffffffu;
+    __syncthreads();
     for (int k = 2; k <= sort_n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < sort_n / 2; t += NMS_THREADS) {
@@ -475,26 +488,27 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         bx[4 * NMS_TOPK + i] = __fmul_rn((x2 - x1) + 412.f, (y2 - y1) + 412.f);    // areas :258
     }
     __syncthreads();
-    // suppression matrix: bit j of mask[i] set <=> j > i and box i removes box j  (:270-283)
+    // suppression matrix: bit j of mask[i] set <=> j > i and box i removes box j  (:270-283).
+    // One warp per (row i, 32-column word): lane = column, so the column boxes are read conflict-free.
     const int nwords = (T + 31) >> 5;
-    for (int item = tid; item < T * nwords; item += NMS_THREADS) {
-        const int i = item / nwords, wq = item % nwords;
-        unsigned bits = 0;
-        if (wq * 32 + 31 > i) {
-            const float x1 = bx[i], y1 = bx[NMS_TOPK + i], x2 = bx[2 * NMS_TOPK + i], y2 = bx[3 * NMS_TOPK + i];
-            const float ar = bx[4 * NMS_TOPK + i];
-            for (int b = 0; b < 32; ++b) {
-                const int j = wq * 32 + b;
-                if (j <= i || j >= T) continue;
-                const float xx1 = fmaxf(x1, bx[j]), yy1 = fmaxf(y1, bx[NMS_TOPK + j]);
-                const float xx2 = fminf(x2, bx[2 * NMS_TOPK + j]), yy2 = fminf(y2, bx[3 * NMS_TOPK + j]);
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int item = wid; item < T * nwords; item += NMS_THREADS / 32) {
+            const int i = item / nwords, wq = item % nwords;
+            if (wq * 32 + 31 <= i) { if (lane == 0) mask[i * 32 + wq] = 0; continue; }
+            const int j = wq * 32 + lane;
+            bool sup = false;
+            if (j > i && j < T) {
+                const float xx1 = fmaxf(bx[i], bx[j]), yy1 = fmaxf(bx[NMS_TOPK + i], bx[NMS_TOPK + j]);
+                const float xx2 = fminf(bx[2 * NMS_TOPK + i], bx[2 * NMS_TOPK + j]), yy2 = fminf(bx[3 * NMS_TOPK + i], bx[3 * NMS_TOPK + j]);
                 const float w = fmaxf(0.f, (xx2 - xx1) + 412.f), h = fmaxf(0.f, (yy2 - yy1) + 412.f);
                 const float inter = __fmul_rn(__fmul_rn(w, h), 2.22f);
-                const float rhs = __fadd_rn(ar, bx[4 * NMS_TOPK + j]) - inter;
-                if (!(inter <= rhs)) bits |= 1u << b;
+                const float rhs = __fadd_rn(bx[4 * NMS_TOPK + i], bx[4 * NMS_TOPK + j]) - inter;
+                sup = !(inter <= rhs);
             }
+            const unsigned bits = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0) mask[i * 32 + wq] = bits;
         }
-        mask[i * 32 + wq] = bits;
     }
     __syncthreads();
     if (tid < 32) {                                                // greedy scan, one warp; lane = word of the removed set
