@@ -316,8 +316,7 @@ static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, flo
             a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
             a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
             a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
-            const size_t npix = (size_t)n * a.Hout * a.Wout;
-            conv_p1_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(a);
+            conv_p1_kernel<<<dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), 256, 0, st>>>(a);
             break;
         }
         case OP_CONV: {

@@ -58,6 +58,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {       // wait_group takes an immediate
+    switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+    }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -103,14 +115,14 @@ struct TcParams {
     int nkc_pad;       // nkc rounded up to even
     int tmem_cols;     // power of two >= max(32, 2 * cout)
     int resident_b;    // 1: all weights stay in smem for the life of the CTA
+    int lag;           // producer stages in flight before the oldest is published (1 <= lag < NS)
     int bw_log, bh_log;            // tile box: 2^bw_log x 2^bh_log x (128 >> (bw_log + bh_log)) pixels (x, y, image)
     int tiles_x, tiles_y, ntiles;
 };
 
 constexpr int TC_PRODUCERS = 128;
 constexpr int TC_THREADS = 448;        // 4 producer + 8 epilogue + MMA + loader warps
-constexpr int TC_MAX_NS = 6;
-constexpr int TC_LAG = 2;              // producer stages in flight before the oldest is published (< NS)
+constexpr int TC_MAX_NS = 8;
 
 struct ChunkRec { long long off; int tap; int pad_; };     // byte offset incl. plane and tap shift; tap bit index
 
@@ -254,6 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         // ===== producers: im2col gather, one output pixel (GEMM row) per thread =====
         const int dx = tid & ((1 << tp.bw_log) - 1), dy = (tid >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = tid >> (tp.bw_log + tp.bh_log);
         const uint32_t dst_row = smem_u32(sA) + tid * 16;
+        const int lag = tp.lag;
         int g = 0;                                               // global stage counter (runs across tiles)
         for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
@@ -279,16 +292,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
                     cp_async16(dst0 + c * 2048, ok ? base + k.off : a.ws, ok ? 16u : 0u);
                 }
                 cp_async_commit();
-                if (g >= TC_LAG) {
-                    cp_async_wait<TC_LAG>();
+                if (g >= lag) {
+                    cp_async_wait_dyn(lag);
                     fence_proxy_async();
-                    mbar_arrive(full0 + 8 * ((g - TC_LAG) % NS));
+                    mbar_arrive(full0 + 8 * ((g - lag) % NS));
                 }
             }
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        for (int s = (g > TC_LAG ? g - TC_LAG : 0); s < g; ++s) mbar_arrive(full0 + 8 * (s % NS));
+        for (int s = (g > lag ? g - lag : 0); s < g; ++s) mbar_arrive(full0 + 8 * (s % NS));
     } else if (warp < 12) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int grp = (warp - 4) >> 2;                         // tile parity this group drains
@@ -406,7 +419,8 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /
     tp.tiles_y = a.Hout >> bh_log;
     tp.ntiles = tp.tiles_x * tp.tiles_y * ((a.n + bn - 1) / bn);
     tp.nkc_pad = (a.nkc + 1) & ~1;
-    tp.KS = tp.nkc_pad < 8 ? tp.nkc_pad : 8;
+    const int ks_max = N <= 64 ? 16 : 8;                         // 32 KB / 16 KB of A per stage
+    tp.KS = tp.nkc_pad < ks_max ? tp.nkc_pad : ks_max;
     tp.nst = (tp.nkc_pad + tp.KS - 1) / tp.KS;
     int cols = 32;
     while (cols < 2 * N) cols <<= 1;
@@ -414,13 +428,16 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /
     const size_t lut_bytes = a.epi == 0 ? (size_t)(2 * a.M + 1) * 4 : 0;
     const size_t fixed = (size_t)a.nkc * sizeof(tc::ChunkRec) + (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
-    const size_t budget = 200 * 1024;
+    const size_t budget = 208 * 1024;
     tp.resident_b = w_bytes <= 96 * 1024 ? 1 : 0;
-    const size_t a_stage = (size_t)tp.KS * 2048, b_stage = (size_t)tp.KS * N * 16;
-    int ns = 4;
-    while (ns > 3 && fixed + (tp.resident_b ? w_bytes + ns * a_stage : ns * (a_stage + b_stage)) > budget) --ns;
+    const size_t per_stage = (size_t)tp.KS * 2048 + (tp.resident_b ? 0 : (size_t)tp.KS * N * 16);
+    const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
+    int ns = (int)(avail / per_stage);
+    if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
+    if (ns < 2) return 1;
     tp.NS = ns;
-    const size_t smem = fixed + (tp.resident_b ? w_bytes + ns * a_stage : ns * (a_stage + b_stage));
+    tp.lag = ns - 1 < 7 ? ns - 1 : 7;                             // deep prefetch: the small-K layers are latency bound
+    const size_t smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_stage;
     if (smem > 224 * 1024) return 1;
     unsigned grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     tc::conv_tc_kernel<<<grid, tc::TC_THREADS, smem, st>>>(a, tp);

@@ -158,58 +158,66 @@ struct P1Args {
     int* acc_tap;
 };
 
-__global__ void __launch_bounds__(128) conv_p1_kernel(const P1Args a) {
-    __shared__ uint4 sW[16][2];
+// grid (Wout/32, Hout/8, n), block 256: one 32x8 output tile.  The fp32 input patch (3 x 17 x 65) is read with
+// coalesced loads, quantised once (quant_matrix) and kept in smem as one packed word (c0,c1,c2,0) per pixel.
+#define P1_TW 32
+#define P1_TH 8
+__global__ void __launch_bounds__(256) conv_p1_kernel(const P1Args a) {
+    __shared__ unsigned sQ[2 * P1_TH + 1][2 * P1_TW + 2];       // +1 pad word per row
+    __shared__ __align__(16) unsigned sW4[9][16];                // [tap][cout] = (w_c0, w_c1, w_c2, 0)
     __shared__ float lut_s[1024];
-    if (threadIdx.x < 32) sW[threadIdx.x >> 1][threadIdx.x & 1] = ((const uint4*)a.w)[threadIdx.x];
-    for (int i = threadIdx.x; i < 2 * a.M + 1; i += 128) lut_s[i] = a.lut[i];
-    __syncthreads();
-    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
-    const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;
-    if (p >= npix) return;
-    const int ox = (int)(p % a.Wout);
-    const int oy = (int)((p / a.Wout) % a.Hout);
-    const int img = (int)(p / ((size_t)a.Wout * a.Hout));
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    if (tid < 144) {
+        const int tap = tid / 16, co = tid % 16;
+        const int8_t* w = a.w + co * 32 + tap * 3;
+        sW4[tap][co] = pack4(w[0], w[1], w[2], 0);
+    }
+    for (int i = tid; i < 2 * a.M + 1; i += 256) lut_s[i] = a.lut[i];
     // quant_matrix: a = max|x|, s = scale(a, k) = M / a evaluated by torch as reciprocal(a) * M (Tensor.__rtruediv__),
     // q = rint(fl32(clip(x) * s))   (utils/quant_matrix_torch.py:57-70, utils/scale.py:4-5)
     const float amax = a.amax[img];
     const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);
-    int q[28];
-#pragma unroll
-    for (int i = 0; i < 28; ++i) q[i] = 0;
     const float* base = a.img + (size_t)img * 3 * a.H * a.W;
+    const size_t cs = (size_t)a.H * a.W;
+    for (int i = tid; i < (2 * P1_TH + 1) * (2 * P1_TW + 1); i += 256) {
+        const int r = i / (2 * P1_TW + 1), c = i % (2 * P1_TW + 1);
+        const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + c;
+        unsigned wd = 0;
+        if ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W && amax > 0.f) {
+            const float* px = base + (size_t)iy * a.W + ix;
+            int q[3];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int iy = 2 * oy + ky - 1;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ix = 2 * ox + kx - 1;
-            const bool ok = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W && amax > 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float x = ok ? __ldg(base + ((size_t)c * a.H + iy) * a.W + ix) : 0.f;
-                x = fminf(fmaxf(x, -amax), amax);
-                q[(ky * 3 + kx) * 3 + c] = ok ? __float2int_rn(__fmul_rn(x, s)) : 0;
+            for (int ch = 0; ch < 3; ++ch) {
+                const float x = fminf(fmaxf(__ldg(px + ch * cs), -amax), amax);
+                q[ch] = __float2int_rn(__fmul_rn(x, s));
             }
+            wd = pack4(q[0], q[1], q[2], 0);
         }
+        sQ[r][c] = wd;
     }
-    int wd[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) wd[i] = (int)pack4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+    __syncthreads();
+    const int tx = tid & (P1_TW - 1), ty = tid / P1_TW;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox >= a.Wout || oy >= a.Hout) return;
     int acc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint4 w0 = sW[j][0], w1 = sW[j][1];
-        int sacc = __ldg(a.bias + j);
-        sacc = __dp4a(wd[0], (int)w0.x, sacc);
-        sacc = __dp4a(wd[1], (int)w0.y, sacc);
-        sacc = __dp4a(wd[2], (int)w0.z, sacc);
-        sacc = __dp4a(wd[3], (int)w0.w, sacc);
-        sacc = __dp4a(wd[4], (int)w1.x, sacc);
-        sacc = __dp4a(wd[5], (int)w1.y, sacc);
-        sacc = __dp4a(wd[6], (int)w1.z, sacc);
-        acc[j] = sacc;
-    }
+    for (int j = 0; j < 16; ++j) acc[j] = __ldg(a.bias + j);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int v = (int)sQ[2 * ty + ky][2 * tx + kx];
+            const uint4* wr = (const uint4*)sW4[ky * 3 + kx];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 wv = wr[q4];
+                acc[4 * q4] = __dp4a(v, (int)wv.x, acc[4 * q4]);
+                acc[4 * q4 + 1] = __dp4a(v, (int)wv.y, acc[4 * q4 + 1]);
+                acc[4 * q4 + 2] = __dp4a(v, (int)wv.z, acc[4 * q4 + 2]);
+                acc[4 * q4 + 3] = __dp4a(v, (int)wv.w, acc[4 * q4 + 3]);
+            }
+        }
     if (a.acc_tap) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) a.acc_tap[(((size_t)img * 16 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(128) conv_p1_kernel(const P1Args a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
         r[j] = silu_q(acc[j], __ldg(a.tab + j), __ldg(a.tab + 16 + j), __ldg(a.tab + 32 + j), __ldg(a.tab + 48 + j), lut_s, a.M);
+    const size_t p = ((size_t)img * a.Hout + oy) * a.Wout + ox;
     *(uint4*)(a.out + p * 16) = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]),
                                            pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
 }
@@ -413,14 +422,51 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     unsigned* keys = (unsigned*)smem_raw;                          // [16384]
     unsigned* mask = keys + NMS_SORT_N;                            // [1000][32]
     float* bx = (float*)(mask + NMS_TOPK * 32);                    // [5][1000]: x1 y1 x2 y2 area (class-offset boxes)
-    int* sh = (int*)(bx + 5 * NMS_TOPK);                           // [0]=ncand [1]=nkeep
+    int* sh = (int*)(bx + 5 * NMS_TOPK);                           // [0]=nsorted [1]=nkeep [2]=ncand [3..5] selection scratch
     __shared__ int kept[NMS_TOPK];
     const int img = blockIdx.x, tid = threadIdx.x, A = a.A;
     const int* conf = a.mode == 0 ? a.conf + (size_t)img * A : nullptr;
-    if (tid == 0) { sh[0] = 0; sh[1] = 0; }
+    if (tid < 8) sh[tid] = 0;
     __syncthreads();
-    // candidates: conf > 8192 (:299,:302,:327); key orders by (conf desc, index asc).  Keys are appended in any
-    // order (the index inside the key makes the order total), then sorted.
+    // candidates: conf > 8192 (:299,:302,:327).  Only the 1000 best survive argsort(...)[:1000] (:260), so first find
+    // the score c* of the 1000th best with a two-level histogram (score >> 9, score & 511) and sort only candidates
+    // with score >= c* (all ties at c* are kept: the index inside the key decides among them, as a stable sort would).
+    int* hist = (int*)mask;                                         // [256] + [512], the mask region is still unused
+    for (int i = tid; i < 768; i += NMS_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < A; i += NMS_THREADS) {
+        const int c = a.mode == 0 ? conf[i] : (int)a.scores[i];
+        if (a.mode != 0 || c > 8192) atomicAdd(&hist[c >> 9], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cstar = 0, total = 0;
+        for (int b = 0; b < 256; ++b) total += hist[b];
+        if (total > NMS_TOPK) {
+            int above = 0, b1 = 255;
+            for (; b1 > 0 && above + hist[b1] < NMS_TOPK; --b1) above += hist[b1];
+            sh[3] = b1; sh[4] = above;
+        } else {
+            sh[3] = -1;
+        }
+        sh[5] = cstar;
+    }
+    __syncthreads();
+    if (sh[3] >= 0) {
+        const int b1 = sh[3];
+        for (int i = tid; i < A; i += NMS_THREADS) {
+            const int c = a.mode == 0 ? conf[i] : (int)a.scores[i];
+            if ((a.mode != 0 || c > 8192) && (c >> 9) == b1) atomicAdd(&hist[256 + (c & 511)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int above = sh[4], b2 = 511;
+            for (; b2 > 0 && above + hist[256 + b2] < NMS_TOPK; --b2) above += hist[256 + b2];
+            sh[5] = (b1 << 9) | b2;
+        }
+        __syncthreads();
+    }
+    const int cstar = sh[5];
     for (int i0 = 0; i0 < A; i0 += NMS_THREADS) {                  // warp-uniform trip count
         const int i = i0 + tid;
         unsigned key = 0;
@@ -428,11 +474,11 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         if (i < A) {
             if (a.mode == 0) {
                 const int c = conf[i];
-                cand = c > 8192;
+                cand = c > 8192 && c >= cstar;
                 key = ((unsigned)(32767 - c) << 14) | (unsigned)i;
             } else {
                 const int c = (int)a.scores[i];                    // host wrapper guarantees 0 <= c <= 131071, integer
-                cand = true;
+                cand = c >= cstar;
                 key = ((unsigned)(131071 - c) << 14) | (unsigned)i;
             }
         }
@@ -447,7 +493,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         }
     }
     __syncthreads();
-    const int ncand = sh[0];
+    const int ncand = sh[0];                                       // candidates that entered the sort (>= min(total, 1000))
     if (ncand == 0) {                                              // reference: coord_quant returns None -> (None, None)
         if (tid == 0) a.counts[img] = 0;
         return;

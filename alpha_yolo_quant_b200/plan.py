@@ -445,6 +445,9 @@ class Plan:
         self.n_ops = len(builder.ops)
         self.n_acc_taps = builder.n_acc_taps
         self.taps = builder.taps
+        by_op = {meta['op']: nm for nm, meta in builder.info['layers'].items()}
+        generic = {OP_POOL: 'sppf_pool', OP_HEAD: 'head(dfl+scores)', OP_NMS: 'q_NMS'}
+        self.op_names = [by_op.get(i, generic.get(op[0], f'op{i}')) for i, op in enumerate(builder.ops)]
 
 
 def compile_plan(state_dict, all_scales, max_a_dict, K=8, sigmoid_range=6, taps=False):

@@ -235,9 +235,7 @@ def main():
         e.set_profiling(False)
         peaks = load_peaks()
         rows = []
-        names = ['absmax(quant_matrix)'] + [None] * p.n_ops
-        for nm, meta in p.info['layers'].items():
-            names[1 + meta['op']] = nm
+        names = ['absmax(quant_matrix)'] + list(p.op_names)
         passes_per_step = (B + args.max_batch - 1) // args.max_batch
         for i in range(len(op_ms)):
             if op_calls[i] == 0:
@@ -254,15 +252,24 @@ def main():
             rows.append(row)
         rows.sort(key=lambda r: -r['avg_ms'])
         top = rows[0]
-        if 'macs_per_img' in top:
-            inten = top['macs_per_img'] / top['bytes_per_img']
-            if inten >= 250:
-                peak = 2 * peaks['bf16_sus']
-                roofline = {'bound': 'tensor', 'achieved': top['tops'], 'peak': peak, 'unit': 'TOP/s (int8; peak = 2 x ' + peaks['src'] + ' sustained bf16)',
-                            'frac': top['tops'] / peak, 'traffic': None, 'kernel': top['op']}
-            else:
-                roofline = {'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': top['gbs'] / peaks['hbm'],
-                            'traffic': None, 'kernel': top['op'], 'peak_source': peaks['src']}
+        # Dominant kernel = the convolution kernel (one kernel, 62 launches per pass, ~85 % of the pass).  SURVEY.md 8(d):
+        # the network is HBM-bound at 1 B/activation (219 OP/B against a ~500 OP/B ridge), so the roofline is algorithmic
+        # bytes (every conv input plane read once + every output plane written once) over the measured launch time.
+        conv_rows = [r for r in rows if 'macs_per_img' in r and r['op'] != 'Conv_P1']
+        if conv_rows:
+            imgs = min(B, args.max_batch)
+            t_ms = sum(r['avg_ms'] for r in conv_rows)
+            byt = sum(r['bytes_per_img'] for r in conv_rows) * imgs
+            mac = sum(r['macs_per_img'] for r in conv_rows) * imgs
+            gbs = 1e-6 * byt / t_ms
+            kname = 'conv_tc_kernel' if args.conv == 'tcgen05' else 'conv_dp4a_kernel'
+            roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
+                        'traffic': None, 'kernel': kname, 'launches_per_pass': len(conv_rows),
+                        'avg_launch_us': 1e3 * t_ms / len(conv_rows), 'algorithmic_bytes_per_launch': byt / len(conv_rows),
+                        'share_of_pass': float(sum(r['share'] for r in conv_rows)), 'peak_source': peaks['src'],
+                        'tensor': {'achieved': 2e-9 * mac / t_ms, 'peak': 2 * peaks['bf16_sus'], 'unit': 'TOP/s int8 (peak = 2 x sustained bf16)',
+                                   'frac': 2e-9 * mac / t_ms / (2 * peaks['bf16_sus'])},
+                        'note': 'aggregate over all launches of the kernel in one pass: sum of algorithmic bytes / sum of event-timed durations'}
         if args.ops_json:
             json.dump({'rows': rows, 'batch_per_pass': min(B, args.max_batch), 'conv': args.conv}, open(args.ops_json, 'w'), indent=1)
 
