@@ -156,7 +156,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     memcpy(&h, p, sizeof h);
     if (h.magic != AYQ_MAGIC) return fail(-22, "ayq_create: bad magic 0x%x", h.magic);
     if (h.version != AYQ_PLAN_VERSION) return fail(-22, "ayq_create: plan version %u, library %d", h.version, AYQ_PLAN_VERSION);
-    if (h.K < 2 || h.K > 9) return fail(-22, "ayq_create: unsupported bit width K=%d (2..9)", h.K);
+    if (h.K < 2 || h.K > 8) return fail(-22, "ayq_create: unsupported bit width K=%d (2..8: activations are stored as int8)", h.K);
     if (h.data_off + h.data_bytes > nbytes || h.ops_off + (uint64_t)h.n_ops * sizeof(OpDesc) > nbytes ||
         h.bufs_off + (uint64_t)h.n_bufs * sizeof(BufDesc) > nbytes)
         return fail(-22, "ayq_create: truncated plan (%zu bytes)", nbytes);
@@ -270,14 +270,14 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
     if (e->conv_impl == 1) {
-        int rc = tc_launch_conv(e->tc, a, f, st);
+        int rc = tc_launch_conv(e->tc, a, (const float*)(e->host_data.data() + f[CF_TAB_OFF]), (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), st);
         if (rc == 0) return 0;
         if (rc != 1) return fail(-5, "tcgen05 conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
         // rc == 1: shape not covered by the tcgen05 kernel -> CUDA-core kernel below
     }
     const size_t npix = (size_t)n * a.Hout * a.Wout;
     const unsigned gx = (unsigned)((npix + 127) / 128);
-    const size_t lut_bytes = a.epi == 0 ? (size_t)(2 * a.M + 1) * 4 : 0;   // the sigmoid table is only read by the SiLU epilogue
+    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;       // the sigmoid table is only read by the SiLU epilogue
     if (a.cout % 32 == 0) {
         conv_dp4a_kernel<32><<<dim3(gx, a.cout / 32), 128, (size_t)a.nkc * 32 * 16 + lut_bytes, st>>>(a);
     } else {
@@ -309,14 +309,23 @@ static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, flo
         case OP_CONV_P1: {
             P1Args a;
             a.img = img; a.amax = amax;
-            a.w = (const int8_t*)(e->d_data + f[P1_W_OFF]);
-            a.bias = (const int*)(e->d_data + f[P1_BIAS_OFF]);
-            a.tab = (const float*)(e->d_data + f[P1_TAB_OFF]);
             a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
             a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
             a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
             a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
-            conv_p1_kernel<<<dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), 256, 0, st>>>(a);
+            P1Const pc;
+            const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
+            const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);         // [4][16]
+            const int* hb = (const int*)(e->host_data.data() + f[P1_BIAS_OFF]);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int co = 0; co < 16; ++co) {
+                    const int8_t* w = hw + co * 32 + tap * 3;
+                    pc.w4[tap][co] = (unsigned)(uint8_t)w[0] | ((unsigned)(uint8_t)w[1] << 8) | ((unsigned)(uint8_t)w[2] << 16);
+                }
+            for (int co = 0; co < 16; ++co) {
+                pc.k1[co] = ht[co]; pc.i1[co] = ht[16 + co]; pc.k2[co] = ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
+            }
+            conv_p1_kernel<<<dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), 256, 0, st>>>(a, pc);
             break;
         }
         case OP_CONV: {

@@ -105,7 +105,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* r) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait16(int* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
 struct TcParams {
@@ -137,42 +143,67 @@ __device__ __forceinline__ TileCoord tile_coord(int t, const TcParams& tp) {
     return c;
 }
 
-// fixed-point epilogue for 16 consecutive channels of one pixel, per-channel tables in shared memory
-__device__ __forceinline__ void epilogue16_s(const ConvArgs& a, int* acc, int c0, int img, int oy, int ox,
+// Per-channel epilogue coefficients for cout <= 80, passed as a __grid_constant__ kernel parameter: with the channel
+// loop fully unrolled every coefficient is a constant-bank / uniform-register operand (no loads in the inner loop).
+#define TC_CT_MAXN 80
+struct EpiTab { float k1[TC_CT_MAXN], i1[TC_CT_MAXN], k2[TC_CT_MAXN], i2[TC_CT_MAXN]; int bias[TC_CT_MAXN]; };
+
+struct Quad { float k1[4], i1[4], k2[4], i2[4]; int b[4]; };
+__device__ __forceinline__ Quad quad_const(const EpiTab& t, int c) {   // c is a compile-time constant after unrolling
+    Quad q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { q.k1[j] = t.k1[c + j]; q.i1[j] = t.i1[c + j]; q.k2[j] = t.k2[c + j]; q.i2[j] = t.i2[c + j]; q.b[j] = t.bias[c + j]; }
+    return q;
+}
+__device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const int* __restrict__ bias_s, int N, int c) {
+    Quad q;
+    const float4 k1 = *(const float4*)(tab_s + c), i1 = *(const float4*)(tab_s + N + c);
+    const float4 k2 = *(const float4*)(tab_s + 2 * N + c), i2 = *(const float4*)(tab_s + 3 * N + c);
+    const int4 b = *(const int4*)(bias_s + c);
+    q.k1[0] = k1.x; q.k1[1] = k1.y; q.k1[2] = k1.z; q.k1[3] = k1.w;
+    q.i1[0] = i1.x; q.i1[1] = i1.y; q.i1[2] = i1.z; q.i1[3] = i1.w;
+    q.k2[0] = k2.x; q.k2[1] = k2.y; q.k2[2] = k2.z; q.k2[3] = k2.w;
+    q.i2[0] = i2.x; q.i2[1] = i2.y; q.i2[2] = i2.z; q.i2[3] = i2.w;
+    q.b[0] = b.x; q.b[1] = b.y; q.b[2] = b.z; q.b[3] = b.w;
+    return q;
+}
+
+// fixed-point epilogue for 16 consecutive channels [c0, c0+16) of one pixel.  CT: coefficients from the constant bank
+// (c0 compile-time) or from shared memory.  acc[] = raw accumulators (bias not yet added).
+template <int EPI, bool CT>
+__device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
                                              const float* __restrict__ lut_s) {
     const int M = a.M, N = a.cout;
     const size_t npix = (size_t)a.n * a.Hout * a.Wout;
     const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+    int r[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int4 b = *(const int4*)(bias_s + c0 + 4 * q);
-        acc[4 * q] += b.x; acc[4 * q + 1] += b.y; acc[4 * q + 2] += b.z; acc[4 * q + 3] += b.w;
+        const Quad cf = CT ? quad_const(et, c0 + 4 * q) : quad_smem(tab_s, bias_s, N, c0 + 4 * q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = acc[4 * q + j] + cf.b[j];
+            acc[4 * q + j] = v;
+            if (EPI == 0) r[4 * q + j] = silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
+            else if (EPI == 1) r[4 * q + j] = requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);
+            else r[4 * q + j] = requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
+        }
     }
     if (a.acc_tap) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             a.acc_tap[(((size_t)img * N + c0 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
     }
-    if (a.epi == 0) {                 // EPI_SILU
-        int r[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 k1 = *(const float4*)(tab_s + c0 + 4 * q), i1 = *(const float4*)(tab_s + N + c0 + 4 * q);
-            const float4 k2 = *(const float4*)(tab_s + 2 * N + c0 + 4 * q), i2 = *(const float4*)(tab_s + 3 * N + c0 + 4 * q);
-            r[4 * q] = silu_q(acc[4 * q], k1.x, i1.x, k2.x, i2.x, lut_s, M);
-            r[4 * q + 1] = silu_q(acc[4 * q + 1], k1.y, i1.y, k2.y, i2.y, lut_s, M);
-            r[4 * q + 2] = silu_q(acc[4 * q + 2], k1.z, i1.z, k2.z, i2.z, lut_s, M);
-            r[4 * q + 3] = silu_q(acc[4 * q + 3], k1.w, i1.w, k2.w, i2.w, lut_s, M);
-        }
+    if (EPI == 0) {                   // EPI_SILU
         for (int o = 0; o < a.nout; ++o) {
             const OutSpec& os = a.out[o];
             uint32_t wd[4];
             if (os.mode == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    wd[j] = pack4(requant((float)r[4 * j], os.k, os.inv, M), requant((float)r[4 * j + 1], os.k, os.inv, M),
-                                  requant((float)r[4 * j + 2], os.k, os.inv, M), requant((float)r[4 * j + 3], os.k, os.inv, M));
+                    wd[j] = pack4(requant8((float)r[4 * j], os.k, os.inv, M), requant8((float)r[4 * j + 1], os.k, os.inv, M),
+                                  requant8((float)r[4 * j + 2], os.k, os.inv, M), requant8((float)r[4 * j + 3], os.k, os.inv, M));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) wd[j] = pack4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -191,25 +222,13 @@ __device__ __forceinline__ void epilogue16_s(const ConvArgs& a, int* acc, int c0
                 *(uint4*)(pl + (p00 + W2 + 1) * 16) = v;
             }
         }
-    } else if (a.epi == 1) {          // EPI_REQUANT8
-        uint32_t wd[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 k = *(const float4*)(tab_s + c0 + 4 * q), iv = *(const float4*)(tab_s + N + c0 + 4 * q);
-            wd[q] = pack4(requant(__int2float_rn(acc[4 * q]), k.x, iv.x, M), requant(__int2float_rn(acc[4 * q + 1]), k.y, iv.y, M),
-                          requant(__int2float_rn(acc[4 * q + 2]), k.z, iv.z, M), requant(__int2float_rn(acc[4 * q + 3]), k.w, iv.w, M));
-        }
-        *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    } else if (EPI == 1) {            // EPI_REQUANT8
+        *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) =
+            make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
     } else {                          // EPI_REQUANT16
         uint32_t wd[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 k = *(const float4*)(tab_s + c0 + 4 * q), iv = *(const float4*)(tab_s + N + c0 + 4 * q);
-            const int q0 = requant(__int2float_rn(acc[4 * q]), k.x, iv.x, M), q1 = requant(__int2float_rn(acc[4 * q + 1]), k.y, iv.y, M);
-            const int q2 = requant(__int2float_rn(acc[4 * q + 2]), k.z, iv.z, M), q3 = requant(__int2float_rn(acc[4 * q + 3]), k.w, iv.w, M);
-            wd[2 * q] = (uint32_t)(q0 & 0xffff) | ((uint32_t)(q1 & 0xffff) << 16);
-            wd[2 * q + 1] = (uint32_t)(q2 & 0xffff) | ((uint32_t)(q3 & 0xffff) << 16);
-        }
+        for (int j = 0; j < 8; ++j) wd[j] = (uint32_t)(r[2 * j] & 0xffff) | ((uint32_t)(r[2 * j + 1] & 0xffff) << 16);
         uint4* dst = (uint4*)((int16_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16);
         dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
@@ -217,7 +236,11 @@ __device__ __forceinline__ void epilogue16_s(const ConvArgs& a, int* acc, int c0
 }
 
 // dynamic smem: [A ring NS*KS*2048][B: resident nkc_pad*N*16 | ring NS*KS*N*16][chunk table nkc*16][tab 4N f32][bias N i32][lut]
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcParams tp) {
+// NBC > 0: cout = 16 * NBC known at compile time (channel loop unrolled, coefficients from `et`); NBC == 0: any cout,
+// coefficients from shared memory.
+template <int NBC, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
+                                                                const __grid_constant__ EpiTab et) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 5];   // full[NS], empty[NS], tfull[2], tempty[2], wfull
     __shared__ uint32_t tmem_base_s;
@@ -242,10 +265,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         r.pad_ = 0;
         skc[i] = r;
     }
-    for (int i = tid; i < 4 * N; i += TC_THREADS) tab_s[i] = a.tab[i];
-    for (int i = tid; i < N; i += TC_THREADS) bias_s[i] = a.bias[i];
-    if (a.epi == 0)
-        for (int i = tid; i < 2 * a.M + 1; i += TC_THREADS) lut_s[i] = a.lut[i];
+    if (NBC == 0) {
+        for (int i = tid; i < 4 * N; i += TC_THREADS) tab_s[i] = a.tab[i];
+        for (int i = tid; i < N; i += TC_THREADS) bias_s[i] = a.bias[i];
+    }
+    if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TC_THREADS);
     if (tid == 0) {
         const uint32_t full_count = TC_PRODUCERS + (tp.resident_b ? 0 : 1);
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
@@ -316,14 +340,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
             const bool valid = img < a.n;
             mbar_wait(tfull0 + 8 * grp, (it >> 1) & 1);
             tc_fence_after();
-            for (int gch = 0; gch < N / 16; ++gch) {
-                int acc[16];
-                tmem_ld16(lane_base + (uint32_t)(gch * 16), acc);
-                if (gch == N / 16 - 1) {                         // accumulator fully read: hand the buffer back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(tempty0 + 8 * grp);
+            // software pipeline over 16-column groups: the TMEM load of group g+1 is in flight while group g is computed
+            int accA[16], accB[16];
+            tmem_ld16(lane_base, accA);
+            if (NBC > 0) {
+#pragma unroll
+                for (int gch = 0; gch < NBC; ++gch) {
+                    int* cur = (gch & 1) ? accB : accA;
+                    int* nxt = (gch & 1) ? accA : accB;
+                    tmem_ld_wait16(cur);
+                    if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
+                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }   // accumulator fully read: hand it back to the MMA warp
+                    if (valid) epilogue16_t<EPI, true>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
-                if (valid) epilogue16_s(a, acc, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+            } else {
+                const int nb = N / 16;                                   // even (cout 128 / 256 / ...), checked by the host
+                for (int gch = 0; gch < nb; gch += 2) {
+                    tmem_ld_wait16(accA);
+                    tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
+                    if (valid) epilogue16_t<EPI, false>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    tmem_ld_wait16(accB);
+                    if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
+                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }
+                    if (valid) epilogue16_t<EPI, false>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                }
             }
         }
     } else if (warp == 12) {
@@ -393,8 +433,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 
 }  // namespace tc
 
+typedef void (*TcKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab);
+// instantiations: SiLU for every cout; requant8 / requant16 only for the Detect-head output convs (cout 64 / 80)
+static inline TcKernel tc_pick(int N, int epi) {
+    using namespace tc;
+    if (epi == 0) {
+        switch (N) {
+        case 16: return conv_tc_kernel<1, 0>;
+        case 32: return conv_tc_kernel<2, 0>;
+        case 48: return conv_tc_kernel<3, 0>;
+        case 64: return conv_tc_kernel<4, 0>;
+        case 80: return conv_tc_kernel<5, 0>;
+        default: return (N % 32 == 0) ? conv_tc_kernel<0, 0> : nullptr;
+        }
+    }
+    if (epi == 1) return N == 64 ? conv_tc_kernel<4, 1> : (N % 32 == 0 ? conv_tc_kernel<0, 1> : nullptr);
+    if (epi == 2) return N == 80 ? conv_tc_kernel<5, 2> : (N % 32 == 0 ? conv_tc_kernel<0, 2> : nullptr);
+    return nullptr;
+}
+
 static inline void tc_init(TcState& s) {
-    cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    const int ns[] = {16, 32, 48, 64, 80, 128};
+    for (int epi = 0; epi < 3; ++epi)
+        for (int N : ns) {
+            TcKernel k = tc_pick(N, epi);
+            if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -403,10 +467,12 @@ static inline void tc_init(TcState& s) {
 static inline void tc_release(TcState&) {}
 
 // returns 0 = launched, 1 = shape not covered (caller uses the CUDA-core kernel), <0 = error
-static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /*op fields*/, cudaStream_t st) {
+static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_tab /*[4][cout]*/, const int* h_bias, cudaStream_t st) {
     if (!s.ready) return 1;
     const int N = a.cout;
     if (N % 16 != 0 || N < 16 || N > 256) return 1;
+    TcKernel kern = tc_pick(N, a.epi);
+    if (!kern) return 1;
     tc::TcParams tp;
     // tile box: widest power-of-two row segment that divides Wout, then rows, then images
     int bw_log = 4;
@@ -425,7 +491,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /
     int cols = 32;
     while (cols < 2 * N) cols <<= 1;
     tp.tmem_cols = cols;
-    const size_t lut_bytes = a.epi == 0 ? (size_t)(2 * a.M + 1) * 4 : 0;
+    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
     const size_t fixed = (size_t)a.nkc * sizeof(tc::ChunkRec) + (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = 208 * 1024;
@@ -440,7 +506,14 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const int32_t* /
     const size_t smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_stage;
     if (smem > 224 * 1024) return 1;
     unsigned grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
-    tc::conv_tc_kernel<<<grid, tc::TC_THREADS, smem, st>>>(a, tp);
+    tc::EpiTab et;
+    if (N <= TC_CT_MAXN) {
+        for (int c = 0; c < N; ++c) {
+            et.k1[c] = h_tab[c]; et.i1[c] = h_tab[N + c]; et.k2[c] = h_tab[2 * N + c]; et.i2[c] = h_tab[3 * N + c];
+            et.bias[c] = h_bias[c];
+        }
+    }
+    kern<<<grid, tc::TC_THREADS, smem, st>>>(a, tp, et);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -5,33 +5,68 @@
 //   t   = RN32(k * x)                      fp32 product (can exceed 2^31, so no int32 maths)
 //   q   = floor(t / 2^(s-1));  q = floor(q / 2) + q mod 2        ==  floor((t + 2^(s-1)) / 2^s)
 //   out = clamp(q, -M, M)
-// floor(t*2^-s + 1/2) is evaluated as  float2int_rd(fma_rd(t, 2^-s, 0.5)):  the round-DOWN fma can
-// never step over the integer below the exact sum, so the result is exact whenever it lies inside
-// the int32 range, and saturates (then clamps to +-M) outside it.  All products use __fmul_rn so
-// that nvcc cannot contract them.
+// floor(t*2^-s + 1/2) is evaluated as  cvt.rmi(fma_rd(t, 2^-s, 0.5)):  the round-DOWN fma can never
+// step over the integer below the exact sum, so the floor is exact; the conversion saturates at the
+// destination width (int32 / int16 / int8), which is harmless because the result is clamped to +-M
+// (M <= 127 for activations, 32767 for the 16-bit logits) right after.  All products use __fmul_rn
+// so that nvcc cannot contract them.
+//
+// The hot epilogues use the narrow conversions: cvt.rmi.sat.s8.f32 (SASS F2I.S8.FLOOR) gives
+// clamp(floor(x), -128, 127) in one instruction, so an activation requant costs
+// FMUL + FFMA.RM + F2I.S8 + max(-M) [+ min(M) when M < 127].
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace ayq {
 
+// ---- generic (any clamp up to 2^23): used by the fp32 layer-library kernels ---------------------------
 __device__ __forceinline__ int rq_round(float t, float inv2s, int M) {
     int q = __float2int_rd(__fmaf_rd(t, inv2s, 0.5f));
     return max(-M, min(M, q));
 }
-
-// requantize(): x is an integer carried in fp32 (exact below 2^24, like the reference)
 __device__ __forceinline__ int requant(float x, float k, float inv2s, int M) {
     return rq_round(__fmul_rn(k, x), inv2s, M);
 }
 
-// silu(): acc = conv accumulator (+bias); lut[r + M] = sigmoid table entry as float
+// ---- narrow saturating floors ----------------------------------------------------------------------
+__device__ __forceinline__ int floor_sat_s8(float x) {       // clamp(floor(x), -128, 127)
+    int r;
+    asm("cvt.rmi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ int floor_sat_s16(float x) {      // clamp(floor(x), -32768, 32767)
+    int r;
+    asm("cvt.rmi.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// requantize() to an activation width (M <= 127)
+__device__ __forceinline__ int requant8(float x, float k, float inv2s, int M) {
+    return max(-M, min(M, floor_sat_s8(__fmaf_rd(__fmul_rn(k, x), inv2s, 0.5f))));
+}
+// requantize() to 16 bits (M = 32767)
+__device__ __forceinline__ int requant16(float x, float k, float inv2s) {
+    return max(-32767, floor_sat_s16(__fmaf_rd(__fmul_rn(k, x), inv2s, 0.5f)));
+}
+
+// ---- silu() -----------------------------------------------------------------------------------------
+// 256-entry sigmoid table indexed by the SATURATED first requant:  lut256[i] = table[clamp(i - 128, -M, M)],
+// so the first clamp of silu() is folded into the table (fill_lut256 below).
+#define AYQ_LUT256 256
+__device__ __forceinline__ void fill_lut256(float* __restrict__ dst, const float* __restrict__ table /*[2M+1]*/, int M,
+                                            int tid, int nthreads) {
+    for (int i = tid; i < AYQ_LUT256; i += nthreads) {
+        const int r = max(-M, min(M, i - 128));
+        dst[i] = table[r + M];
+    }
+}
+// acc = conv accumulator (+bias).  Returns the K-bit activation in [-M, M].
 __device__ __forceinline__ int silu_q(int acc, float k1, float i1, float k2, float i2,
-                                      const float* __restrict__ lut, int M) {
-    float a = __int2float_rn(acc);
-    int r1 = rq_round(__fmul_rn(k1, a), i1, M);
-    float pr = __fmul_rn(lut[r1 + M], a);          // res_silu *= res_conv_copy (fp32), round() is a no-op
-    return rq_round(__fmul_rn(k2, pr), i2, M);
+                                      const float* __restrict__ lut256, int M) {
+    const float a = __int2float_rn(acc);
+    const int r1 = floor_sat_s8(__fmaf_rd(__fmul_rn(k1, a), i1, 0.5f));
+    const float pr = __fmul_rn(lut256[r1 + 128], a);       // res_silu *= res_conv_copy (fp32), round() is a no-op
+    return max(-M, min(M, floor_sat_s8(__fmaf_rd(__fmul_rn(k2, pr), i2, 0.5f))));
 }
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
