@@ -49,6 +49,7 @@ struct ayq_engine {
     std::vector<size_t> buf_off;           // per buffer, for `cap`
     size_t off_amax = 0, off_dbox = 0, off_conf = 0, off_cls = 0, off_stage = 0;
     std::vector<KChunk*> d_kc;             // per op (device), rebuilt when cap changes
+    std::vector<std::vector<KChunk>> h_kc; // per op (host copy)
     std::vector<int*> acc_taps;            // per tap device buffers (cap images)
     std::vector<size_t> acc_tap_elems;     // per image
     int conv_impl = 0;
@@ -109,6 +110,7 @@ static int ensure_workspace(ayq_engine* e, int n) {
     e->cap = cap;
     // resolve K-chunk tables and accumulator taps
     e->d_kc.assign(e->ops.size(), nullptr);
+    e->h_kc.assign(e->ops.size(), std::vector<KChunk>());
     int ntaps = 0;
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const int32_t* f = e->ops[i].f;
@@ -127,6 +129,7 @@ static int ensure_workspace(ayq_engine* e, int n) {
             }
             CK(cudaMalloc(&e->d_kc[i], sizeof(KChunk) * nkc));
             CK(cudaMemcpy(e->d_kc[i], kc.data(), sizeof(KChunk) * nkc, cudaMemcpyHostToDevice));
+            e->h_kc[i] = kc;
             tap = f[CF_ACC_TAP];
             elems = (size_t)f[CF_COUT] * f[CF_HOUT] * f[CF_WOUT];
         } else if (f[0] == OP_CONV_P1) {
@@ -270,7 +273,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
     if (e->conv_impl == 1) {
-        int rc = tc_launch_conv(e->tc, a, (const float*)(e->host_data.data() + f[CF_TAB_OFF]), (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), st);
+        int rc = tc_launch_conv(e->tc, a, e->h_kc[opi].data(), (const float*)(e->host_data.data() + f[CF_TAB_OFF]), (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), st);
         if (rc == 0) return 0;
         if (rc != 1) return fail(-5, "tcgen05 conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
         // rc == 1: shape not covered by the tcgen05 kernel -> CUDA-core kernel below

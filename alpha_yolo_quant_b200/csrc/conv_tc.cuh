@@ -67,7 +67,12 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {       // wait_group t
     case 4: cp_async_wait<4>(); break;
     case 5: cp_async_wait<5>(); break;
     case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    case 10: cp_async_wait<10>(); break;
+    case 11: cp_async_wait<11>(); break;
+    default: cp_async_wait<12>(); break;
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -124,22 +129,31 @@ struct TcParams {
     int lag;           // producer stages in flight before the oldest is published (1 <= lag < NS)
     int bw_log, bh_log;            // tile box: 2^bw_log x 2^bh_log x (128 >> (bw_log + bh_log)) pixels (x, y, image)
     int tiles_x, tiles_y, ntiles;
+    unsigned mul_x, mul_y;         // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y)  (0 when the divisor is 1)
 };
 
 constexpr int TC_PRODUCERS = 128;
 constexpr int TC_THREADS = 448;        // 4 producer + 8 epilogue + MMA + loader warps
-constexpr int TC_MAX_NS = 8;
+constexpr int TC_MAX_NS = 16;
+constexpr int TC_MAX_LAG = 12;
 
-struct ChunkRec { long long off; int tap; int pad_; };     // byte offset incl. plane and tap shift; tap bit index
+// K chunks grouped by (source buffer, tap): `np` consecutive 16-channel planes that share one address offset and one
+// padding predicate.  The table is a __grid_constant__ kernel parameter, so the producer loop reads it through the
+// constant bank / uniform registers instead of dependent shared-memory loads.
+#define TC_MAX_GROUPS 40
+struct KGroup { long long off; int tap; int np; };     // byte offset incl. buffer, first plane and tap shift
+struct GroupTab { int ngroups; int pad_[3]; KGroup g[TC_MAX_GROUPS]; };
+
+__device__ __forceinline__ unsigned fastdiv(unsigned t, unsigned mul) { return mul ? __umulhi(t, mul) : t; }
 
 struct TileCoord { int img0, y0, x0; };
 __device__ __forceinline__ TileCoord tile_coord(int t, const TcParams& tp) {
     TileCoord c;
-    const int tx = t % tp.tiles_x;
-    const int r = t / tp.tiles_x;
-    c.x0 = tx << tp.bw_log;
-    c.y0 = (r % tp.tiles_y) << tp.bh_log;
-    c.img0 = (r / tp.tiles_y) << (7 - tp.bw_log - tp.bh_log);
+    const unsigned r = fastdiv((unsigned)t, tp.mul_x);            // t / tiles_x   (exact: t * tiles_x < 2^32)
+    const unsigned q = fastdiv(r, tp.mul_y);                      // r / tiles_y
+    c.x0 = (int)((unsigned)t - r * (unsigned)tp.tiles_x) << tp.bw_log;
+    c.y0 = (int)(r - q * (unsigned)tp.tiles_y) << tp.bh_log;
+    c.img0 = (int)q << (7 - tp.bw_log - tp.bh_log);
     return c;
 }
 
@@ -235,12 +249,12 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
     }
 }
 
-// dynamic smem: [A ring NS*KS*2048][B: resident nkc_pad*N*16 | ring NS*KS*N*16][chunk table nkc*16][tab 4N f32][bias N i32][lut]
+// dynamic smem: [A ring NS*KS*2048][B: resident nkc_pad*N*16 | ring NS*KS*N*16][tab 4N f32][bias N i32][lut 256 f32]
 // NBC > 0: cout = 16 * NBC known at compile time (channel loop unrolled, coefficients from `et`); NBC == 0: any cout,
 // coefficients from shared memory.
 template <int NBC, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
-                                                                const __grid_constant__ EpiTab et) {
+                                                                const __grid_constant__ EpiTab et, const __grid_constant__ GroupTab gt) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 5];   // full[NS], empty[NS], tfull[2], tempty[2], wfull
     __shared__ uint32_t tmem_base_s;
@@ -250,21 +264,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     unsigned char* sA = smem;
     unsigned char* sB = smem + (size_t)NS * a_stage_bytes;
     const size_t b_bytes = tp.resident_b ? (size_t)tp.nkc_pad * N * 16 : (size_t)NS * b_stage_bytes;
-    ChunkRec* skc = (ChunkRec*)(sB + b_bytes);
-    float* tab_s = (float*)(skc + a.nkc);
+    float* tab_s = (float*)(sB + b_bytes);
     int* bias_s = (int*)(tab_s + 4 * N);
     float* lut_s = (float*)(bias_s + N);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
     const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
 
-    for (int i = tid; i < a.nkc; i += TC_THREADS) {
-        const KChunk k = a.kc[i];
-        ChunkRec r;
-        r.off = k.off + (long long)k.plane * (long long)a.in_plane_bytes + ((long long)k.dy * a.Win + k.dx) * 16;
-        r.tap = (k.dy + 1) * 3 + (k.dx + 1);          // 1x1 convs: dy = dx = 0 -> tap 4 (centre, always inside)
-        r.pad_ = 0;
-        skc[i] = r;
-    }
     if (NBC == 0) {
         for (int i = tid; i < 4 * N; i += TC_THREADS) tab_s[i] = a.tab[i];
         for (int i = tid; i < N; i += TC_THREADS) bias_s[i] = a.bias[i];
@@ -290,8 +295,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===== producers: im2col gather, one output pixel (GEMM row) per thread =====
         const int dx = tid & ((1 << tp.bw_log) - 1), dy = (tid >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = tid >> (tp.bw_log + tp.bh_log);
         const uint32_t dst_row = smem_u32(sA) + tid * 16;
-        const int lag = tp.lag;
-        int g = 0;                                               // global stage counter (runs across tiles)
+        const int lag = tp.lag, nkc = a.nkc, ngroups = gt.ngroups;
+        const long long plane_bytes = (long long)a.in_plane_bytes;
+        int g = 0;                     // stages issued so far (runs across tiles)
+        int slot = 0;                  // ring slot of the stage being filled = g % NS
+        int pub = 0;                   // ring slot of the next stage to publish = (g - lag) % NS
+        uint32_t ephase = 1;           // parity to wait for on empty[slot]; the first lap passes immediately (fresh barrier)
         for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
@@ -304,41 +313,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int tx = 0; tx < 3; ++tx)
                     if (valid && (unsigned)(iy0 + ty - 1) < (unsigned)a.Hin && (unsigned)(ix0 + tx - 1) < (unsigned)a.Win) tapmask |= 1u << (ty * 3 + tx);
             const int8_t* base = a.ws + (((size_t)(valid ? img : 0) * a.Hin + iy0) * a.Win + ix0) * 16;
-            for (int st = 0; st < nst; ++st, ++g) {
-                const int slot = g % NS;
-                if (g >= NS) mbar_wait(empty0 + 8 * slot, ((g / NS) - 1) & 1);
-                const uint32_t dst0 = dst_row + slot * a_stage_bytes;
-                const int kc0 = st * KS;
-                const int kend = min(KS, a.nkc - kc0);           // an odd tail chunk has zero weights: skip it
-                for (int c = 0; c < kend; ++c) {
-                    const ChunkRec k = skc[kc0 + c];
-                    const bool ok = (tapmask >> k.tap) & 1u;
-                    cp_async16(dst0 + c * 2048, ok ? base + k.off : a.ws, ok ? 16u : 0u);
-                }
-                cp_async_commit();
-                if (g >= lag) {
-                    cp_async_wait_dyn(lag);
-                    fence_proxy_async();
-                    mbar_arrive(full0 + 8 * ((g - lag) % NS));
+            mbar_wait(empty0 + 8 * slot, ephase);
+            uint32_t dst = dst_row + slot * a_stage_bytes;
+            int cs = 0, c = 0;                                   // chunks in the current stage / in the tile
+            for (int gi = 0; gi < ngroups; ++gi) {
+                const KGroup kg = gt.g[gi];
+                const bool ok = (tapmask >> kg.tap) & 1u;        // 1x1 convs use tap 4 (centre): inside whenever the pixel is valid
+                const int8_t* src = ok ? base + kg.off : a.ws;
+                const uint32_t bytes = ok ? 16u : 0u;            // zero fill = conv padding
+                const long long step = ok ? plane_bytes : 0;
+                for (int p = 0; p < kg.np; ++p) {
+                    cp_async16(dst, src, bytes);
+                    src += step; dst += 2048; ++c;
+                    if (++cs == KS && c < nkc) {                 // stage full, more chunks follow in this tile
+                        cp_async_commit();
+                        if (g >= lag) {
+                            cp_async_wait_dyn(lag);
+                            fence_proxy_async();
+                            mbar_arrive(full0 + 8 * pub);
+                            if (++pub == NS) pub = 0;
+                        }
+                        ++g;
+                        if (++slot == NS) { slot = 0; ephase ^= 1; }
+                        mbar_wait(empty0 + 8 * slot, ephase);
+                        dst = dst_row + slot * a_stage_bytes;
+                        cs = 0;
+                    }
                 }
             }
+            cp_async_commit();                                    // last (possibly partial) stage of the tile
+            if (g >= lag) {
+                cp_async_wait_dyn(lag);
+                fence_proxy_async();
+                mbar_arrive(full0 + 8 * pub);
+                if (++pub == NS) pub = 0;
+            }
+            ++g;
+            if (++slot == NS) { slot = 0; ephase ^= 1; }
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        for (int s = (g > lag ? g - lag : 0); s < g; ++s) mbar_arrive(full0 + 8 * (s % NS));
+        for (int s = (g > lag ? g - lag : 0); s < g; ++s) {
+            mbar_arrive(full0 + 8 * pub);
+            if (++pub == NS) pub = 0;
+        }
     } else if (warp < 12) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int grp = (warp - 4) >> 2;                         // tile parity this group drains
         const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * N);
-        int it = 0;
-        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, ++it) {
-            if ((it & 1) != grp) continue;
+        uint32_t tphase = 0;
+        for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x, tphase ^= 1) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
-            mbar_wait(tfull0 + 8 * grp, (it >> 1) & 1);
+            mbar_wait(tfull0 + 8 * grp, tphase);
             tc_fence_after();
             // software pipeline over 16-column groups: the TMEM load of group g+1 is in flight while group g is computed
             int accA[16], accB[16];
@@ -371,16 +401,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) {
             const uint32_t idesc = make_idesc_i8(N);
             if (tp.resident_b) mbar_wait(wfull, 0);
-            int g = 0, it = 0;
-            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x, ++it) {
-                const int b = it & 1;
-                mbar_wait(tempty0 + 8 * b, ((it >> 1) & 1) ^ 1);   // fresh barrier: parity 1 passes immediately
+            int slot = 0, b = 0;
+            uint32_t fphase = 0, ephase = 3;                       // bit b = parity to wait for on tempty[b]; fresh barriers: parity 1 passes
+            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+                mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
+                ephase ^= 1u << b;
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)(b * N);
                 uint32_t accum = 0;
-                for (int st = 0; st < nst; ++st, ++g) {
-                    const int slot = g % NS;
-                    mbar_wait(full0 + 8 * slot, (g / NS) & 1);
+                for (int st = 0; st < nst; ++st) {
+                    mbar_wait(full0 + 8 * slot, fphase);
                     tc_fence_after();
                     const uint32_t abase = smem_u32(sA) + slot * a_stage_bytes;
                     const uint32_t bbase = smem_u32(sB) + (tp.resident_b ? (uint32_t)st : (uint32_t)slot) * b_stage_bytes;
@@ -392,8 +422,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         accum = 1;
                     }
                     mma_commit(empty0 + 8 * slot);            // frees the smem slot when these MMAs retire
+                    if (++slot == NS) { slot = 0; fphase ^= 1; }
                 }
                 mma_commit(tfull0 + 8 * b);                    // accumulator complete -> epilogue group b
+                b ^= 1;
             }
         }
         __syncwarp();
@@ -408,15 +440,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
                 }
             } else {
-                int g = 0;
+                int slot = 0;
+                uint32_t ephase = 1;
                 for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
-                    for (int st = 0; st < nst; ++st, ++g) {
-                        const int slot = g % NS;
-                        if (g >= NS) mbar_wait(empty0 + 8 * slot, ((g / NS) - 1) & 1);
+                    for (int st = 0; st < nst; ++st) {
+                        mbar_wait(empty0 + 8 * slot, ephase);
                         const int chunks = min(KS, tp.nkc_pad - st * KS);
                         const uint32_t bytes = (uint32_t)chunks * N * 16u;
                         mbar_arrive_expect_tx(full0 + 8 * slot, bytes);
                         bulk_g2s(smem_u32(sB) + slot * b_stage_bytes, a.w + (size_t)st * KS * N * 16, bytes, full0 + 8 * slot);
+                        if (++slot == NS) { slot = 0; ephase ^= 1; }
                     }
                 }
             }
@@ -433,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
 }  // namespace tc
 
-typedef void (*TcKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab);
+typedef void (*TcKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::GroupTab);
 // instantiations: SiLU for every cout; requant8 / requant16 only for the Detect-head output convs (cout 64 / 80)
 static inline TcKernel tc_pick(int N, int epi) {
     using namespace tc;
@@ -467,7 +500,10 @@ static inline void tc_init(TcState& s) {
 static inline void tc_release(TcState&) {}
 
 // returns 0 = launched, 1 = shape not covered (caller uses the CUDA-core kernel), <0 = error
-static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_tab /*[4][cout]*/, const int* h_bias, cudaStream_t st) {
+static inline unsigned tc_magic(int d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)d - 1) / (unsigned)d); }
+
+// h_kc: the op's K-chunk list on the host (buffer byte offset, plane, dy, dx relative to the padded origin)
+static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const KChunk* h_kc, const float* h_tab /*[4][cout]*/, const int* h_bias, cudaStream_t st) {
     if (!s.ready) return 1;
     const int N = a.cout;
     if (N % 16 != 0 || N < 16 || N > 256) return 1;
@@ -484,6 +520,24 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_t
     tp.tiles_x = a.Wout >> bw_log;
     tp.tiles_y = a.Hout >> bh_log;
     tp.ntiles = tp.tiles_x * tp.tiles_y * ((a.n + bn - 1) / bn);
+    tp.mul_x = tc_magic(tp.tiles_x); tp.mul_y = tc_magic(tp.tiles_y);
+    if ((unsigned long long)tp.ntiles * (unsigned)tp.tiles_x >= (1ull << 32)) return 1;
+    // group consecutive chunks that differ only by the plane index
+    tc::GroupTab gt;
+    gt.ngroups = 0;
+    for (int i = 0; i < a.nkc; ++i) {
+        const KChunk& k = h_kc[i];
+        if (gt.ngroups > 0 && i > 0 && h_kc[i - 1].off == k.off && h_kc[i - 1].dy == k.dy && h_kc[i - 1].dx == k.dx &&
+            h_kc[i - 1].plane + 1 == k.plane) {
+            ++gt.g[gt.ngroups - 1].np;
+            continue;
+        }
+        if (gt.ngroups == TC_MAX_GROUPS) return 1;
+        tc::KGroup& g = gt.g[gt.ngroups++];
+        g.off = k.off + (long long)k.plane * (long long)a.in_plane_bytes + ((long long)k.dy * a.Win + k.dx) * 16;
+        g.tap = (k.dy + 1) * 3 + (k.dx + 1);           // 1x1 convs: dy = dx = 0 -> tap 4 (centre, always inside)
+        g.np = 1;
+    }
     tp.nkc_pad = (a.nkc + 1) & ~1;
     const int ks_max = N <= 64 ? 16 : 8;                         // 32 KB / 16 KB of A per stage
     tp.KS = tp.nkc_pad < ks_max ? tp.nkc_pad : ks_max;
@@ -492,7 +546,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_t
     while (cols < 2 * N) cols <<= 1;
     tp.tmem_cols = cols;
     const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
-    const size_t fixed = (size_t)a.nkc * sizeof(tc::ChunkRec) + (size_t)N * 20 + lut_bytes + 64;
+    const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = 208 * 1024;
     tp.resident_b = w_bytes <= 96 * 1024 ? 1 : 0;
@@ -502,7 +556,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_t
     if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
     if (ns < 2) return 1;
     tp.NS = ns;
-    tp.lag = ns - 1 < 7 ? ns - 1 : 7;                             // deep prefetch: the small-K layers are latency bound
+    tp.lag = ns / 2 < 1 ? 1 : (ns / 2 > tc::TC_MAX_LAG ? tc::TC_MAX_LAG : ns / 2);   // loads in flight vs stages buffered for the MMA warp
     const size_t smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_stage;
     if (smem > 224 * 1024) return 1;
     unsigned grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
@@ -513,7 +567,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const float* h_t
             et.bias[c] = h_bias[c];
         }
     }
-    kern<<<grid, tc::TC_THREADS, smem, st>>>(a, tp, et);
+    kern<<<grid, tc::TC_THREADS, smem, st>>>(a, tp, et, gt);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -1,5 +1,5 @@
 """Attribute executed warp-instructions / stall samples of one profiled kernel to CUDA source lines.
-   python tools/ncu_lines.py <rep> <kernel-regex> <launch index> [libayq.so]
+   python tools/ncu_lines.py <rep> <kernel-regex> <launch index> [mangled-name substring] [libayq.so]
 Joins `ncu --page source` (per SASS address) with `nvdisasm -g` line info of the cubin inside the .so."""
 import collections
 import csv
@@ -10,7 +10,7 @@ import sys
 import tempfile
 
 
-def main(rep, kre, idx, so='alpha_yolo_quant_b200/libayq.so'):
+def main(rep, kre, idx, fnpat=None, so='alpha_yolo_quant_b200/libayq.so'):
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
@@ -38,7 +38,7 @@ def main(rep, kre, idx, so='alpha_yolo_quant_b200/libayq.so'):
     h, data = b[0], b[1:]
     iA, iI, iSm = h.index('Address'), h.index('Instructions Executed'), h.index('# Samples')
     base = int(data[0][iA], 16)
-    fn = [f for (f, _) in line_of if kre.split('|')[0] in f]
+    fn = [f for (f, _) in line_of if (fnpat or kre.split('|')[0]) in f]
     fn = fn[0] if fn else None
     ex, sm = collections.Counter(), collections.Counter()
     for r in data:
