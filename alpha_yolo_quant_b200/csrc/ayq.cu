@@ -16,6 +16,7 @@
 #include "plan_format.h"
 #include "kernels.cuh"
 #include "conv_tc.cuh"
+#include "conv_tma.cuh"
 
 using namespace ayq;
 
@@ -69,7 +70,10 @@ struct ayq_engine {
     std::vector<float> op_ms;
     std::vector<int> op_calls;
     std::vector<cudaEvent_t> prof_ev;
-    TcState tc;                            // tcgen05 path state (tensor maps etc.)
+    TcState tc;                            // tcgen05 path state
+    TmaState tma;                          // TMA-fed tcgen05 path: driver entry point for tensor-map encoding
+    std::vector<TmaLaunch> tma_cache;      // per op: tensor maps + stage plan for the last pass size
+    std::vector<std::vector<TmaSeg>> tma_segs;   // per op: source buffers of the conv input
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -111,6 +115,8 @@ static int ensure_workspace(ayq_engine* e, int n) {
     // resolve K-chunk tables and accumulator taps
     e->d_kc.assign(e->ops.size(), nullptr);
     e->h_kc.assign(e->ops.size(), std::vector<KChunk>());
+    e->tma_cache.assign(e->ops.size(), TmaLaunch());
+    e->tma_segs.assign(e->ops.size(), std::vector<TmaSeg>());
     int ntaps = 0;
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const int32_t* f = e->ops[i].f;
@@ -120,12 +126,22 @@ static int ensure_workspace(ayq_engine* e, int n) {
             const int32_t* src = (const int32_t*)(e->host_data.data() + f[CF_KC_OFF]);
             const int pad = f[CF_KSIZE] / 2;
             std::vector<KChunk> kc(nkc);
+            std::vector<int> seg_buf;
             for (int k = 0; k < nkc; ++k) {
-                kc[k].off = (long long)e->buf_off[src[4 * k]];
+                const int buf = src[4 * k];
+                kc[k].off = (long long)e->buf_off[buf];
                 kc[k].plane = src[4 * k + 1];
                 kc[k].dy = src[4 * k + 2] - pad;
                 kc[k].dx = src[4 * k + 3] - pad;
-                kc[k].pad_ = 0;
+                int sg = -1;
+                for (size_t q = 0; q < seg_buf.size(); ++q) if (seg_buf[q] == buf) sg = (int)q;
+                if (sg < 0) {
+                    sg = (int)seg_buf.size();
+                    seg_buf.push_back(buf);
+                    TmaSeg ts; ts.base = e->ws + e->buf_off[buf]; ts.nplanes = e->bufs[buf].nplanes;
+                    e->tma_segs[i].push_back(ts);
+                }
+                kc[k].pad_ = sg;                               // index into tma_segs[op]
             }
             CK(cudaMalloc(&e->d_kc[i], sizeof(KChunk) * nkc));
             CK(cudaMemcpy(e->d_kc[i], kc.data(), sizeof(KChunk) * nkc, cudaMemcpyHostToDevice));
@@ -185,6 +201,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     tc_init(e->tc);
+    tma_init(e->tma);
     e->op_ms.assign(h.n_ops + 1, 0.f);
     e->op_calls.assign(h.n_ops + 1, 0);
     *out = e;
@@ -220,7 +237,7 @@ extern "C" int ayq_set_max_batch(ayq_handle e, int max_batch) {
 }
 extern "C" size_t ayq_workspace_bytes(ayq_handle e) { return e ? e->ws_bytes : 0; }
 extern "C" int ayq_set_conv_impl(ayq_handle e, int impl) {
-    if (!e || impl < 0 || impl > 1) return fail(-22, "ayq_set_conv_impl: 0 (dp4a) or 1 (tcgen05)");
+    if (!e || impl < 0 || impl > 2) return fail(-22, "ayq_set_conv_impl: 0 (dp4a), 1 (tcgen05, cp.async feed) or 2 (tcgen05, TMA feed)");
     e->conv_impl = impl;
     return 0;
 }
@@ -272,7 +289,18 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
         a.out[o].up = of[5];
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
-    if (e->conv_impl == 1) {
+    if (e->conv_impl == 2) {
+        TmaLaunch& L = e->tma_cache[opi];
+        const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
+        const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
+        if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias);
+        if (L.ok) {
+            if (tma_launch(L, a, st) == 0) return 0;
+            return fail(-5, "TMA conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
+        }
+        // shape not covered by the TMA kernel -> cp.async-fed tcgen05 kernel below
+    }
+    if (e->conv_impl >= 1) {
         int rc = tc_launch_conv(e->tc, a, e->h_kc[opi].data(), (const float*)(e->host_data.data() + f[CF_TAB_OFF]), (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), st);
         if (rc == 0) return 0;
         if (rc != 1) return fail(-5, "tcgen05 conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));

@@ -1,0 +1,373 @@
+// conv_tma.cuh -- TMA-fed variant of the tcgen05 / TMEM implicit-GEMM quantised convolution (sm_100a).
+//
+// Same GEMM view, tiles, B layout, TMEM double buffering and fixed-point epilogue as conv_tc.cuh; what changes is the
+// A-operand feed.  Activation buffers are 16-channel planes [plane][n][H][W][16 B], i.e. a rank-5 uint8 tensor
+// {16, W, H, n, planes}.  For one K-chunk group (source buffer, filter tap, np consecutive planes) ONE tensor-map TMA
+// (cp.async.bulk.tensor.5d) with box {16, bw*s, bh*s, bn, np} and element strides {1, s, s, 1, 1} lands exactly np K-chunks
+// of the A tile in shared memory, each [128 pixels][16 B] = the canonical K-major no-swizzle core-matrix layout:
+//   * the filter tap is the box origin (x0*s + kx - pad, y0*s + ky - pad): out-of-range coordinates are zero filled
+//     by the hardware, which IS the convolution padding (and the image overhang of the last tile);
+//   * the convolution stride is the TMA element stride;
+//   * concat / residual-sum inputs are further groups from other tensor maps (plan.py's segment lists).
+// One elected thread issues the loads (no producer warps, no per-pixel address arithmetic, no proxy fences); stages are
+// packed on the host from whole boxes.  Warp roles: warp 0 = TMA producer (A, and B when the weights are streamed),
+// warp 1 = MMA issuer + TMEM allocator, warp 2 = resident-weight loader, warps 4-7 / 8-11 = epilogue of even / odd tiles.
+#pragma once
+#include <cuda.h>
+#include "conv_tc.cuh"
+
+namespace ayq {
+
+namespace tc {
+
+constexpr int TMA_MAX_MAPS = 8;
+constexpr int TMA_MAX_OPS = 56;
+constexpr int TMA_MAX_STAGES = 24;
+constexpr int TMA_THREADS = 384;
+
+struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box origin offsets (tap - pad), first plane, byte offset in the slot
+struct TmaStage { int op0, nops, nchunks, chunk0; };
+struct TmaPlan {
+    int nstages, nops, stride, slot_chunks;                            // slot_chunks = K chunks one ring slot can hold
+    TmaStage st[TMA_MAX_STAGES];
+    TmaOp op[TMA_MAX_OPS];
+};
+struct TmaMaps { CUtensorMap m[TMA_MAX_MAPS]; };
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
+
+// dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
+template <int NBC, int EPI>
+__global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
+                                                                  const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
+                                                                  const __grid_constant__ TmaMaps maps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 5];   // full[NS], empty[NS], tfull[2], tempty[2], wfull
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.cout, NS = tp.NS;
+    const uint32_t a_slot_bytes = (uint32_t)pl.slot_chunks * 2048u, b_slot_bytes = (uint32_t)pl.slot_chunks * N * 16u;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + (size_t)NS * a_slot_bytes;
+    const size_t b_bytes = tp.resident_b ? (size_t)tp.nkc_pad * N * 16 : (size_t)NS * b_slot_bytes;
+    float* tab_s = (float*)(sB + b_bytes);
+    int* bias_s = (int*)(tab_s + 4 * N);
+    float* lut_s = (float*)(bias_s + N);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
+
+    if (NBC == 0) {
+        for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
+        for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i];
+    }
+    if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        mbar_init(wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)tp.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer: one thread, one tensor load per K-chunk group =====
+        if (lane == 0) {
+            const int nstages = pl.nstages, stride = pl.stride;
+            int slot = 0;
+            uint32_t ephase = 1;                                   // fresh barrier: parity 1 passes immediately
+            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+                const TileCoord tc0 = tile_coord(t, tp);
+                const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
+                for (int s = 0; s < nstages; ++s) {
+                    const TmaStage sg = pl.st[s];
+                    mbar_wait(empty0 + 8 * slot, ephase);
+                    const uint32_t bar = full0 + 8 * slot;
+                    const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
+                    mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
+                    const uint32_t dst0 = smem_u32(sA) + slot * a_slot_bytes;
+                    for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
+                        const TmaOp op = pl.op[o];
+                        tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
+                    }
+                    if (!tp.resident_b)
+                        bulk_g2s(smem_u32(sB) + slot * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
+                    if (++slot == NS) { slot = 0; ephase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(N);
+            const int nstages = pl.nstages;
+            if (tp.resident_b) mbar_wait(wfull, 0);
+            int slot = 0, b = 0;
+            uint32_t fphase = 0, ephase = 3;                       // bit b = parity to wait for on tempty[b]
+            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+                mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
+                ephase ^= 1u << b;
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + (uint32_t)(b * N);
+                uint32_t accum = 0;
+                for (int s = 0; s < nstages; ++s) {
+                    const TmaStage sg = pl.st[s];
+                    mbar_wait(full0 + 8 * slot, fphase);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA) + slot * a_slot_bytes;
+                    const uint32_t bbase = smem_u32(sB) + (tp.resident_b ? (uint32_t)sg.chunk0 * N * 16u : slot * b_slot_bytes);
+                    const int pairs = (sg.nchunks + 1) >> 1;      // an odd tail pairs with stale smem x zero weights
+                    for (int j = 0; j < pairs; ++j) {
+                        const uint64_t ad = make_desc(abase + j * 4096, 2048, 128);
+                        const uint64_t bd = make_desc(bbase + j * 2 * N * 16, N * 16, 128);
+                        mma_i8(dcol, ad, bd, idesc, accum);
+                        accum = 1;
+                    }
+                    mma_commit(empty0 + 8 * slot);                // frees the smem slot when these MMAs retire
+                    if (++slot == NS) { slot = 0; fphase ^= 1; }
+                }
+                mma_commit(tfull0 + 8 * b);                        // accumulator complete -> epilogue group b
+                b ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== resident weights: one bulk-TMA burst at kernel start =====
+        if (lane == 0 && tp.resident_b) {
+            const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
+            mbar_arrive_expect_tx(wfull, total);
+            for (uint32_t o = 0; o < total; o += 32768u) {
+                const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
+                bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
+        const int grp = (warp - 4) >> 2;                         // tile parity this group drains
+        const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
+        const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * N);
+        uint32_t tphase = 0;
+        for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x, tphase ^= 1) {
+            const TileCoord tc0 = tile_coord(t, tp);
+            const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
+            const bool valid = img < a.n;
+            mbar_wait(tfull0 + 8 * grp, tphase);
+            tc_fence_after();
+            int accA[16], accB[16];
+            tmem_ld16(lane_base, accA);
+            if (NBC > 0) {
+#pragma unroll
+                for (int gch = 0; gch < NBC; ++gch) {
+                    int* cur = (gch & 1) ? accB : accA;
+                    int* nxt = (gch & 1) ? accA : accB;
+                    tmem_ld_wait16(cur);
+                    if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
+                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }   // accumulator fully read: hand it back to the MMA warp
+                    if (valid) epilogue16_t<EPI, true>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                }
+            } else {
+                const int nb = N / 16;                                   // even, checked by the host
+                for (int gch = 0; gch < nb; gch += 2) {
+                    tmem_ld_wait16(accA);
+                    tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
+                    if (valid) epilogue16_t<EPI, false>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    tmem_ld_wait16(accB);
+                    if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
+                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }
+                    if (valid) epilogue16_t<EPI, false>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tp.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmaLaunch {            // everything one launch needs, cached per (op, images in the pass)
+    int n = -1;               // images the cache was built for (-1 = empty), 0 = shape not covered
+    int ok = 0;
+    tc::TcParams tp;
+    tc::EpiTab et;
+    tc::TmaPlan pl;
+    tc::TmaMaps maps;
+    size_t smem = 0;
+    unsigned grid = 0;
+};
+
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; };
+
+typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
+static inline TmaKernel tma_pick(int N, int epi) {
+    using namespace tc;
+    if (epi == 0) {
+        switch (N) {
+        case 16: return conv_tma_kernel<1, 0>;
+        case 32: return conv_tma_kernel<2, 0>;
+        case 64: return conv_tma_kernel<4, 0>;
+        case 80: return conv_tma_kernel<5, 0>;
+        default: return (N % 32 == 0) ? conv_tma_kernel<0, 0> : nullptr;
+        }
+    }
+    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1> : (N % 32 == 0 ? conv_tma_kernel<0, 1> : nullptr);
+    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2> : (N % 32 == 0 ? conv_tma_kernel<0, 2> : nullptr);
+    return nullptr;
+}
+
+static inline void tma_init(TmaState& s) {
+    const int ns[] = {16, 32, 64, 80, 128};
+    for (int epi = 0; epi < 3; ++epi)
+        for (int N : ns) {
+            TmaKernel k = tma_pick(N, epi);
+            if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) {
+        s.encode = (PFN_tmapEncodeTiled)fn;
+        s.ready = 1;
+    }
+    cudaGetLastError();
+}
+
+// One buffer segment of the conv input as the TMA sees it.
+struct TmaSeg { const void* base; int nplanes; };   // base = first byte of the buffer (plane 0), planes in the buffer
+
+// Build the launch record.  h_kc: K-chunk list (pad_ = index into segs).  Returns L.ok.
+static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, const KChunk* h_kc, const TmaSeg* segs, int nsegs,
+                              const float* h_tab, const int* h_bias) {
+    L.n = a.n; L.ok = 0;
+    if (!s.ready) return 0;
+    const int N = a.cout;
+    if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi)) return 0;
+    tc::TcParams& tp = L.tp;
+    int bw_log = 4;
+    while (bw_log > 0 && (a.Wout % (1 << bw_log))) --bw_log;
+    int bh_log = 7 - bw_log;
+    while (bh_log > 0 && (a.Hout % (1 << bh_log))) --bh_log;
+    tp.bw_log = bw_log; tp.bh_log = bh_log;
+    const int bn = 128 >> (bw_log + bh_log);
+    tp.tiles_x = a.Wout >> bw_log;
+    tp.tiles_y = a.Hout >> bh_log;
+    tp.ntiles = tp.tiles_x * tp.tiles_y * ((a.n + bn - 1) / bn);
+    tp.mul_x = tc_magic(tp.tiles_x); tp.mul_y = tc_magic(tp.tiles_y);
+    if ((unsigned long long)tp.ntiles * (unsigned)tp.tiles_x >= (1ull << 32)) return 0;
+    if ((1 << bw_log) * a.stride > 256 || (1 << bh_log) * a.stride > 256 || bn > 256) return 0;
+    tp.nkc_pad = (a.nkc + 1) & ~1;
+    const int slot_chunks = N <= 64 ? 16 : 8;                    // 32 KB / 16 KB of A per ring slot
+    tp.KS = slot_chunks; tp.nst = 0; tp.lag = 0;
+    int cols = 32;
+    while (cols < 2 * N) cols <<= 1;
+    tp.tmem_cols = cols;
+
+    // groups -> boxes (power-of-two plane counts, so that a stage never ends on an odd chunk before the tile's last stage)
+    tc::TmaPlan& pl = L.pl;
+    pl.nstages = 0; pl.nops = 0; pl.stride = a.stride; pl.slot_chunks = slot_chunks;
+    struct MapKey { int seg, boxp; };
+    MapKey keys[tc::TMA_MAX_MAPS];
+    int nmaps = 0;
+    int stage_chunks = 0, chunk = 0;
+    auto open_stage = [&]() -> bool {
+        if (pl.nstages == tc::TMA_MAX_STAGES) return false;
+        tc::TmaStage& st = pl.st[pl.nstages++];
+        st.op0 = pl.nops; st.nops = 0; st.nchunks = 0; st.chunk0 = chunk;
+        stage_chunks = 0;
+        return true;
+    };
+    if (!open_stage()) return 0;
+    int i = 0;
+    while (i < a.nkc) {
+        int np = 1;
+        while (i + np < a.nkc && h_kc[i + np].pad_ == h_kc[i].pad_ && h_kc[i + np].dy == h_kc[i].dy && h_kc[i + np].dx == h_kc[i].dx &&
+               h_kc[i + np].plane == h_kc[i].plane + np) ++np;
+        int done = 0;
+        while (done < np) {                                       // split the group into power-of-two boxes; fill every slot to capacity
+            if (stage_chunks == slot_chunks && !open_stage()) return 0;   // (so only the tile's last stage can hold an odd chunk count)
+            int bp = 1;
+            while (bp * 2 <= np - done && bp * 2 <= slot_chunks - stage_chunks) bp *= 2;
+            int m = -1;
+            for (int q = 0; q < nmaps; ++q) if (keys[q].seg == h_kc[i].pad_ && keys[q].boxp == bp) m = q;
+            if (m < 0) {
+                if (nmaps == tc::TMA_MAX_MAPS) return 0;
+                m = nmaps++;
+                keys[m].seg = h_kc[i].pad_; keys[m].boxp = bp;
+            }
+            if (pl.nops == tc::TMA_MAX_OPS) return 0;
+            tc::TmaOp& op = pl.op[pl.nops++];
+            op.map = m; op.dx = h_kc[i].dx; op.dy = h_kc[i].dy; op.p0 = h_kc[i].plane + done; op.dst_off = (uint32_t)stage_chunks * 2048u;
+            tc::TmaStage& st = pl.st[pl.nstages - 1];
+            ++st.nops; st.nchunks += bp;
+            stage_chunks += bp; chunk += bp; done += bp;
+        }
+        i += np;
+    }
+    // tensor maps: rank 5 uint8 {16, W, H, n, planes}
+    for (int q = 0; q < nmaps; ++q) {
+        if (keys[q].seg < 0 || keys[q].seg >= nsegs) return 0;
+        const TmaSeg& sg = segs[keys[q].seg];
+        const cuuint64_t gdim[5] = {16, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.n, (cuuint64_t)sg.nplanes};
+        const cuuint64_t gstr[4] = {16, (cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin * a.Win * 16, (cuuint64_t)a.n * a.Hin * a.Win * 16};
+        const cuuint32_t box[5] = {16, (cuuint32_t)((1 << bw_log) * a.stride), (cuuint32_t)((1 << bh_log) * a.stride), (cuuint32_t)bn, (cuuint32_t)keys[q].boxp};
+        const cuuint32_t estr[5] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1, 1};
+        CUresult r = s.encode(&L.maps.m[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(sg.base), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
+    // shared memory budget
+    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
+    const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
+    const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
+    const size_t budget = 208 * 1024;
+    tp.resident_b = w_bytes <= 96 * 1024 ? 1 : 0;
+    const size_t per_slot = (size_t)slot_chunks * 2048 + (tp.resident_b ? 0 : (size_t)slot_chunks * N * 16);
+    const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
+    int ns = (int)(avail / per_slot);
+    if (ns > 8) ns = 8;
+    if (ns < 2) return 0;
+    tp.NS = ns;
+    L.smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_slot;
+    L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
+    if (N <= TC_CT_MAXN) {
+        for (int c = 0; c < N; ++c) {
+            L.et.k1[c] = h_tab[c]; L.et.i1[c] = h_tab[N + c]; L.et.k2[c] = h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
+            L.et.bias[c] = h_bias[c];
+        }
+    }
+    L.ok = 1;
+    return 1;
+}
+
+static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
+    TmaKernel kern = tma_pick(a.cout, a.epi);
+    kern<<<L.grid, tc::TMA_THREADS, L.smem, st>>>(a, L.tp, L.et, L.pl, L.maps);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace ayq

@@ -174,7 +174,7 @@ class Engine:
         return out
 
     def set_conv_impl(self, impl):
-        check(self.lib.ayq_set_conv_impl(self._h, {'dp4a': 0, 'tcgen05': 1}.get(impl, impl)))
+        check(self.lib.ayq_set_conv_impl(self._h, {'dp4a': 0, 'tcgen05': 1, 'tma': 2}.get(impl, impl)))
 
     def set_max_batch(self, mb):
         check(self.lib.ayq_set_max_batch(self._h, mb))

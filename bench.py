@@ -138,7 +138,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
     ap.add_argument('--max-batch', type=int, default=64, help='images per internal pass of the engine')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--conv', default=os.environ.get('AYQ_CONV', 'tcgen05'), choices=['dp4a', 'tcgen05'])
+    ap.add_argument('--conv', default=os.environ.get('AYQ_CONV', 'tcgen05'), choices=['dp4a', 'tcgen05', 'tma'])
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU-baseline sample (images)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -262,7 +262,7 @@ def main():
             byt = sum(r['bytes_per_img'] for r in conv_rows) * imgs
             mac = sum(r['macs_per_img'] for r in conv_rows) * imgs
             gbs = 1e-6 * byt / t_ms
-            kname = 'conv_tc_kernel' if args.conv == 'tcgen05' else 'conv_dp4a_kernel'
+            kname = {'tcgen05': 'conv_tc_kernel', 'tma': 'conv_tma_kernel'}.get(args.conv, 'conv_dp4a_kernel')
             roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
                         'traffic': None, 'kernel': kname, 'launches_per_pass': len(conv_rows),
                         'avg_launch_us': 1e3 * t_ms / len(conv_rows), 'algorithmic_bytes_per_launch': byt / len(conv_rows),

@@ -37,7 +37,7 @@ def _images(seeds):
     return torch.from_numpy(synth.to_input_array([synth.synth_image_u8(s) for s in seeds]))
 
 
-IMPLS = ['dp4a', 'tcgen05']
+IMPLS = ['dp4a', 'tcgen05', 'tma']
 
 
 @pytest.mark.parametrize('impl', IMPLS)
