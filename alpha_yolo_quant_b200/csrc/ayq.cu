@@ -382,6 +382,8 @@ static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, flo
             }
             a.lut_exp = (const float*)(e->d_data + f[HD_LUT_EXP_OFF]);
             a.lut16 = (const int16_t*)(e->d_data + f[HD_LUT16_OFF]);
+            a.lo16 = (const int16_t*)(e->d_data + f[HD_LO16_OFF]);
+            a.mono = f[HD_MONO];
             a.dflw = (const int*)(e->d_data + f[HD_DFLW_OFF]);
             a.anchors = (const int*)(e->d_data + f[HD_ANCH_OFF]);
             a.kd = f_from_bits(f[HD_KD]); a.id = f_from_bits(f[HD_ID]);

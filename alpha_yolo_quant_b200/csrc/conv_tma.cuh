@@ -29,6 +29,7 @@ struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box ori
 struct TmaStage { int op0, nops, nchunks, chunk0; };
 struct TmaPlan {
     int nstages, nops, stride, slot_chunks;                            // slot_chunks = K chunks one ring slot can hold
+    int merged_cx, pad_[3];                                            // 1: stride-1 conv, rank-4 maps with (channel, x) merged into one 16*W byte row
     TmaStage st[TMA_MAX_STAGES];
     TmaOp op[TMA_MAX_OPS];
 };
@@ -37,6 +38,11 @@ struct TmaMaps { CUtensorMap m[TMA_MAX_MAPS]; };
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
@@ -97,7 +103,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                     const uint32_t dst0 = smem_u32(sA) + slot * a_slot_bytes;
                     for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
                         const TmaOp op = pl.op[o];
-                        tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
+                        if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
+                        else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
                     }
                     if (!tp.resident_b)
                         bulk_g2s(smem_u32(sB) + slot * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
@@ -288,6 +295,10 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     // groups -> boxes (power-of-two plane counts, so that a stage never ends on an odd chunk before the tile's last stage)
     tc::TmaPlan& pl = L.pl;
     pl.nstages = 0; pl.nops = 0; pl.stride = a.stride; pl.slot_chunks = slot_chunks;
+    // stride 1: a tile row of bw pixels is 16*bw contiguous bytes -> describe (channel, x) as ONE dimension so the TMA moves
+    // 256-byte rows instead of 16-byte ones (the x tap shift becomes a +-16 byte coordinate; dimension 0 cannot be strided,
+    // so stride-2 convs keep the rank-5 form)
+    pl.merged_cx = (a.stride == 1 && (16 << bw_log) <= 256) ? 1 : 0;
     struct MapKey { int seg, boxp; };
     MapKey keys[tc::TMA_MAX_MAPS];
     int nmaps = 0;
@@ -330,13 +341,24 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     for (int q = 0; q < nmaps; ++q) {
         if (keys[q].seg < 0 || keys[q].seg >= nsegs) return 0;
         const TmaSeg& sg = segs[keys[q].seg];
-        const cuuint64_t gdim[5] = {16, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.n, (cuuint64_t)sg.nplanes};
-        const cuuint64_t gstr[4] = {16, (cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin * a.Win * 16, (cuuint64_t)a.n * a.Hin * a.Win * 16};
-        const cuuint32_t box[5] = {16, (cuuint32_t)((1 << bw_log) * a.stride), (cuuint32_t)((1 << bh_log) * a.stride), (cuuint32_t)bn, (cuuint32_t)keys[q].boxp};
-        const cuuint32_t estr[5] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1, 1};
-        CUresult r = s.encode(&L.maps.m[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(sg.base), gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r;
+        if (pl.merged_cx) {
+            const cuuint64_t gdim[4] = {(cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin, (cuuint64_t)a.n, (cuuint64_t)sg.nplanes};
+            const cuuint64_t gstr[3] = {(cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin * a.Win * 16, (cuuint64_t)a.n * a.Hin * a.Win * 16};
+            const cuuint32_t box[4] = {(cuuint32_t)(16 << bw_log), (cuuint32_t)(1 << bh_log), (cuuint32_t)bn, (cuuint32_t)keys[q].boxp};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            r = s.encode(&L.maps.m[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(sg.base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t gdim[5] = {16, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.n, (cuuint64_t)sg.nplanes};
+            const cuuint64_t gstr[4] = {16, (cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin * a.Win * 16, (cuuint64_t)a.n * a.Hin * a.Win * 16};
+            const cuuint32_t box[5] = {16, (cuuint32_t)((1 << bw_log) * a.stride), (cuuint32_t)((1 << bh_log) * a.stride), (cuuint32_t)bn, (cuuint32_t)keys[q].boxp};
+            const cuuint32_t estr[5] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1, 1};
+            r = s.encode(&L.maps.m[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(sg.base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r != CUDA_SUCCESS) return 0;
     }
     for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];

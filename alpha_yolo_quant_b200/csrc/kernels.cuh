@@ -300,6 +300,8 @@ struct HeadArgs {
     const int16_t* cls[3];      // (5 planes, n, H, W, 16) int16
     const float* lut_exp;       // [2^K], index y + 2^K - 1
     const int16_t* lut16;       // [65535], index l + 32767
+    const int16_t* lo16;        // [65535]: smallest logit with the same table value
+    int mono;                   // table is monotone: class max / argmax need two gathers instead of 80
     const int* dflw;            // [16]
     const int* anchors;         // [A][2]
     float kd, id;
@@ -356,17 +358,40 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
     float* full = a.dbox_cls ? a.dbox_cls + (size_t)img * 84 * a.A + an : nullptr;
     if (full) { full[0] = cx; full[(size_t)a.A] = cy; full[(size_t)2 * a.A] = w; full[(size_t)3 * a.A] = h; }
     int best = -1, bj = 0;
+    if (a.mono && !full) {
+        // conf = max_c LUT[l_c] = LUT[max_c l_c]; first arg-max = first class with l_c >= lo16[max logit]   (torch.max :326)
+        int4 r[10];
 #pragma unroll
-    for (int pl = 0; pl < 5; ++pl) {
-        const int4* src = (const int4*)(a.cls[lvl] + ((size_t)pl * plane_px + pix) * 16);
-        const int4 r0 = __ldg(src), r1 = __ldg(src + 1);
-        const int wv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        for (int pl = 0; pl < 5; ++pl) {
+            const int4* src = (const int4*)(a.cls[lvl] + ((size_t)pl * plane_px + pix) * 16);
+            r[2 * pl] = __ldg(src); r[2 * pl + 1] = __ldg(src + 1);
+        }
+        const int* wv = (const int*)r;
+        int m2 = (int)0x80008000;                                  // packed (int16, int16) running maxima
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int l = (int)(int16_t)((wv[j >> 1] >> (16 * (j & 1))) & 0xffff);
-            const int sc = (int)__ldg(a.lut16 + l + 32767);                              // sigmoid_quant(cls, lookup_final) :1250
-            if (full) full[(size_t)(4 + pl * 16 + j) * a.A] = (float)sc;
-            if (sc > best) { best = sc; bj = pl * 16 + j; }                               // first maximum, like torch.max :326
+        for (int q = 0; q < 40; ++q) m2 = __vmaxs2(m2, wv[q]);
+        const int mx = max((int)(short)(m2 & 0xffff), m2 >> 16);
+        best = (int)__ldg(a.lut16 + mx + 32767);
+        const int lo = (int)__ldg(a.lo16 + mx + 32767);
+        bj = 80;
+#pragma unroll
+        for (int q = 39; q >= 0; --q) {
+            if ((wv[q] >> 16) >= lo) bj = 2 * q + 1;
+            if ((int)(short)(wv[q] & 0xffff) >= lo) bj = 2 * q;
+        }
+    } else {
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) {
+            const int4* src = (const int4*)(a.cls[lvl] + ((size_t)pl * plane_px + pix) * 16);
+            const int4 r0 = __ldg(src), r1 = __ldg(src + 1);
+            const int wv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int l = (int)(int16_t)((wv[j >> 1] >> (16 * (j & 1))) & 0xffff);
+                const int sc = (int)__ldg(a.lut16 + l + 32767);                          // sigmoid_quant(cls, lookup_final) :1250
+                if (full) full[(size_t)(4 + pl * 16 + j) * a.A] = (float)sc;
+                if (sc > best) { best = sc; bj = pl * 16 + j; }                           // first maximum, like torch.max :326
+            }
         }
     }
     a.conf[idx] = best;
@@ -407,23 +432,35 @@ struct NmsArgs {
     float* dets;       // mode 0: (n, 300, 6)      mode 1: kept indices as float (max_keep)
     int* counts;       // (n)
 };
-static constexpr size_t NMS_SMEM = (size_t)NMS_SORT_N * 4 + (size_t)NMS_TOPK * 32 * 4 + (size_t)NMS_TOPK * 5 * 4 + 64;
+// dynamic smem: keys[16384] | bx[5][1000] | diag[1024] (histogram scratch before the sort) | rem[32] | sh[8]
+static constexpr size_t NMS_SMEM = (size_t)NMS_SORT_N * 4 + (size_t)NMS_TOPK * 5 * 4 + 1024 * 4 + 32 * 4 + 64;
+
+// box i suppresses box j (:270-283); row i comes from shared memory (warp-uniform broadcast), column j from registers
+__device__ __forceinline__ bool nms_suppresses(const float* __restrict__ bx, int i, float jx1, float jy1, float jx2, float jy2, float jarea) {
+    const float xx1 = fmaxf(bx[i], jx1), yy1 = fmaxf(bx[NMS_TOPK + i], jy1);
+    const float xx2 = fminf(bx[2 * NMS_TOPK + i], jx2), yy2 = fminf(bx[3 * NMS_TOPK + i], jy2);
+    const float w = fmaxf(0.f, (xx2 - xx1) + 412.f), h = fmaxf(0.f, (yy2 - yy1) + 412.f);
+    const float inter = __fmul_rn(__fmul_rn(w, h), 2.22f);
+    const float rhs = __fadd_rn(bx[4 * NMS_TOPK + i], jarea) - inter;
+    return !(inter <= rhs);
+}
 
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* keys = (unsigned*)smem_raw;                          // [16384]
-    unsigned* mask = keys + NMS_SORT_N;                            // [1000][32]
-    float* bx = (float*)(mask + NMS_TOPK * 32);                    // [5][1000]: x1 y1 x2 y2 area (class-offset boxes)
-    int* sh = (int*)(bx + 5 * NMS_TOPK);                           // [0]=nsorted [1]=nkeep [2]=ncand [3..5] selection scratch
+    float* bx = (float*)(keys + NMS_SORT_N);                       // [5][1000]: x1 y1 x2 y2 area (class-offset boxes)
+    unsigned* diag = (unsigned*)(bx + 5 * NMS_TOPK);               // [1024] intra-chunk suppression words (row i: bits j > i of its chunk)
+    unsigned* rem = diag + 1024;                                   // [32]   removed-set, one word per 32-candidate chunk
+    int* sh = (int*)(rem + 32);                                    // [0]=nsorted [1]=nkeep [3..5] selection scratch [6]=keep word
     __shared__ int kept[NMS_TOPK];
     const int img = blockIdx.x, tid = threadIdx.x, A = a.A;
+    const int lane = tid & 31, wid = tid >> 5;
     const int* conf = a.mode == 0 ? a.conf + (size_t)img * A : nullptr;
     if (tid < 8) sh[tid] = 0;
-    __syncthreads();
     // candidates: conf > 8192 (:299,:302,:327).  Only the 1000 best survive argsort(...)[:1000] (:260), so first find
     // the score c* of the 1000th best with a two-level histogram (score >> 9, score & 511) and sort only candidates
     // with score >= c* (all ties at c* are kept: the index inside the key decides among them, as a stable sort would).
-    int* hist = (int*)mask;                                         // [256] + [512], the mask region is still unused
+    int* hist = (int*)diag;                                         // [256] + [512]
     for (int i = tid; i < 768; i += NMS_THREADS) hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < A; i += NMS_THREADS) {
@@ -432,7 +469,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
-        int cstar = 0, total = 0;
+        int total = 0;
         for (int b = 0; b < 256; ++b) total += hist[b];
         if (total > NMS_TOPK) {
             int above = 0, b1 = 255;
@@ -441,7 +478,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         } else {
             sh[3] = -1;
         }
-        sh[5] = cstar;
+        sh[5] = 0;
     }
     __syncthreads();
     if (sh[3] >= 0) {
@@ -476,7 +513,6 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         }
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (bal) {
-            const int lane = tid & 31;
             const int leader = __ffs(bal) - 1;
             int base = 0;
             if (lane == leader) base = atomicAdd(&sh[0], __popc(bal));
@@ -525,45 +561,63 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
         bx[i] = x1; bx[NMS_TOPK + i] = y1; bx[2 * NMS_TOPK + i] = x2; bx[3 * NMS_TOPK + i] = y2;
         bx[4 * NMS_TOPK + i] = __fmul_rn((x2 - x1) + 412.f, (y2 - y1) + 412.f);    // areas :258
     }
+    if (tid < 32) rem[tid] = 0;
     __syncthreads();
-    // suppression matrix: bit j of mask[i] set <=> j > i and box i removes box j  (:270-283).
-    // One warp per (row i, 32-column word): lane = column, so the column boxes are read conflict-free.
-    const int nwords = (T + 31) >> 5;
-    {
-        const int lane = tid & 31, wid = tid >> 5;
-        for (int item = wid; item < T * nwords; item += NMS_THREADS / 32) {
-            const int i = item / nwords, wq = item % nwords;
-            if (wq * 32 + 31 <= i) { if (lane == 0) mask[i * 32 + wq] = 0; continue; }
-            const int j = wq * 32 + lane;
-            bool sup = false;
-            if (j > i && j < T) {
-                const float xx1 = fmaxf(bx[i], bx[j]), yy1 = fmaxf(bx[NMS_TOPK + i], bx[NMS_TOPK + j]);
-                const float xx2 = fminf(bx[2 * NMS_TOPK + i], bx[2 * NMS_TOPK + j]), yy2 = fminf(bx[3 * NMS_TOPK + i], bx[3 * NMS_TOPK + j]);
-                const float w = fmaxf(0.f, (xx2 - xx1) + 412.f), h = fmaxf(0.f, (yy2 - yy1) + 412.f);
-                const float inter = __fmul_rn(__fmul_rn(w, h), 2.22f);
-                const float rhs = __fadd_rn(bx[4 * NMS_TOPK + i], bx[4 * NMS_TOPK + j]) - inter;
-                sup = !(inter <= rhs);
-            }
-            const unsigned bits = __ballot_sync(0xffffffffu, sup);
-            if (lane == 0) mask[i * 32 + wq] = bits;
+    // Greedy suppression (:262-292) in chunks of 32 sorted candidates.  Only rows that are KEPT ever suppress anything,
+    // so instead of the full T x T matrix: (1) the 32 x 32 diagonal blocks (all warps, in parallel), then per chunk
+    // (2) one warp resolves the chunk serially from the removed-set word and the diagonal words, (3) every later chunk's
+    // warp applies the rows kept in this chunk to its own 32 columns.  Work = T*32 + kept*T pair tests, kept <= max_keep.
+    const int nchunk = (T + 31) >> 5;                              // <= 32 = number of warps
+    if (wid < nchunk) {
+        const int j = wid * 32 + lane;
+        const bool jv = j < T;
+        const int jj = jv ? j : 0;
+        const float jx1 = bx[jj], jy1 = bx[NMS_TOPK + jj], jx2 = bx[2 * NMS_TOPK + jj], jy2 = bx[3 * NMS_TOPK + jj], ja = bx[4 * NMS_TOPK + jj];
+        unsigned mine = 0;
+        for (int ii = 0; ii < 32; ++ii) {
+            const int i = wid * 32 + ii;
+            const bool s = jv && i < T && j > i && nms_suppresses(bx, i, jx1, jy1, jx2, jy2, ja);
+            const unsigned bits = __ballot_sync(0xffffffffu, s);
+            if (lane == ii) mine = bits;
         }
+        diag[wid * 32 + lane] = mine;
     }
     __syncthreads();
-    if (tid < 32) {                                                // greedy scan, one warp; lane = word of the removed set
-        unsigned removed = 0;
-        int nk = 0;
-        for (int i = 0; i < T && nk < a.max_keep; ++i) {
-            const unsigned wsel = __shfl_sync(0xffffffffu, removed, i >> 5);
-            if (!((wsel >> (i & 31)) & 1u)) {
-                if (tid == 0) kept[nk] = i;
-                ++nk;
-                if (tid < nwords) removed |= mask[i * 32 + tid];
+    int nk = 0;                                                    // block-uniform
+    for (int c = 0; c < nchunk && nk < a.max_keep; ++c) {
+        if (wid == 0) {
+            unsigned cur = rem[c];
+            const int nrow = min(32, T - c * 32);
+            if (nrow < 32) cur |= 0xffffffffu << nrow;            // rows past T do not exist
+            const unsigned d = diag[c * 32 + lane];
+            unsigned keep = 0;
+            int k = nk;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const unsigned di = __shfl_sync(0xffffffffu, d, i);
+                if (!((cur >> i) & 1u) && k < a.max_keep) { keep |= 1u << i; cur |= di; ++k; }
             }
+            if ((keep >> lane) & 1u) kept[nk + __popc(keep & ((1u << lane) - 1))] = c * 32 + lane;
+            if (lane == 0) sh[6] = (int)keep;
         }
-        if (tid == 0) { sh[1] = nk; a.counts[img] = nk; }
+        __syncthreads();
+        const unsigned keep = (unsigned)sh[6];
+        nk += __popc(keep);
+        if (wid > c && wid < nchunk && keep && nk < a.max_keep) {
+            const int j = wid * 32 + lane;
+            const bool jv = j < T;
+            const int jj = jv ? j : 0;
+            const float jx1 = bx[jj], jy1 = bx[NMS_TOPK + jj], jx2 = bx[2 * NMS_TOPK + jj], jy2 = bx[3 * NMS_TOPK + jj], ja = bx[4 * NMS_TOPK + jj];
+            unsigned acc = 0;
+            for (unsigned m = keep; m; m &= m - 1) {
+                const int i = c * 32 + __ffs(m) - 1;
+                acc |= __ballot_sync(0xffffffffu, jv && nms_suppresses(bx, i, jx1, jy1, jx2, jy2, ja));
+            }
+            if (lane == 0) rem[wid] |= acc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int nk = sh[1];
+    if (tid == 0) a.counts[img] = nk;
     for (int r = tid; r < nk; r += NMS_THREADS) {
         const int i = kept[r];
         const int an = (int)(keys[i] & 0x3fffu);

@@ -9,7 +9,7 @@
 #include <stdint.h>
 
 #define AYQ_MAGIC 0x31515941u      // "AYQ1"
-#define AYQ_PLAN_VERSION 5
+#define AYQ_PLAN_VERSION 6
 
 struct PlanHeader {
     uint32_t magic, version;
@@ -62,4 +62,6 @@ enum { HD_BOX_BUF0 = 1,                // 3 x int8 buffers (4 planes each), P3 P
        HD_LUT16_OFF = 8,               // int16[65535] final sigmoid table, index l + 32767
        HD_DFLW_OFF = 9,                // int32[16] integer dfl.weight
        HD_ANCH_OFF = 10,               // int32[n_anchors][2] quantised anchor points
-       HD_KD = 11, HD_ID = 12 };       // float bits of the dfl requant coefficient and 2^-s
+       HD_KD = 11, HD_ID = 12,         // float bits of the dfl requant coefficient and 2^-s
+       HD_LO16_OFF = 13,               // int16[65535]: smallest logit with the same final-sigmoid value, index l + 32767
+       HD_MONO = 14 };                 // 1 when the final sigmoid table is monotone non-decreasing

@@ -24,7 +24,7 @@ from . import lut as _lut
 
 DFL_RANGE = 14.8264799118042          # stage_8_torch_full_quant.py:436,473
 MAGIC = 0x31515941
-VERSION = 5
+VERSION = 6
 OP_FIELDS = 64
 OP_CONV, OP_CONV_P1, OP_POOL, OP_HEAD, OP_NMS = 1, 2, 3, 4, 5
 EPI_SILU, EPI_REQUANT8, EPI_REQUANT16 = 0, 1, 2
@@ -395,6 +395,15 @@ class PlanBuilder:
         f[9] = self.add_data(dflw.astype(np.int32))
         f[10] = self.add_data(anchors.astype(np.int32))
         f[11], f[12] = self.fbits(kd[0]), self.fbits(idd[0])
+        # The final sigmoid table is monotone, so max_c LUT[l_c] = LUT[max_c l_c] and the first arg-max class is the first
+        # class whose logit reaches lo16[max logit] = the smallest logit with the same table value (one gather per anchor
+        # instead of 80).  f[14] tells the kernel whether the table really is monotone (else it looks every class up).
+        l16 = lut16.astype(np.int64)
+        mono = bool(np.all(np.diff(l16) >= 0))
+        first = np.concatenate([[True], l16[1:] != l16[:-1]])
+        lo_idx = np.maximum.accumulate(np.where(first, np.arange(l16.size), 0))
+        f[13] = self.add_data((lo_idx - 32767).astype(np.int16))
+        f[14] = 1 if mono else 0
         self.ops.append(f)
         f = [0] * OP_FIELDS
         f[0] = OP_NMS
