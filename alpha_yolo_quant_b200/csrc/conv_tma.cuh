@@ -10,8 +10,9 @@
 //   * the convolution stride is the TMA element stride;
 //   * concat / residual-sum inputs are further groups from other tensor maps (plan.py's segment lists).
 // One elected thread issues the loads (no producer warps, no per-pixel address arithmetic, no proxy fences); stages are
-// packed on the host from whole boxes.  Warp roles: warp 0 = TMA producer (A, and B when the weights are streamed),
-// warp 1 = MMA issuer + TMEM allocator, warp 2 = resident-weight loader, warps 4-7 / 8-11 = epilogue of even / odd tiles.
+// packed on the host from whole boxes.  Warp roles: warps 0, 2, 3 = TMA producers (stages round-robin;
+// A, and B when the weights are streamed; warp 2 also loads resident weights), warp 1 = MMA issuer + TMEM allocator,
+// warps 4-7 / 8-11 = epilogue of even / odd tiles.
 #pragma once
 #include <cuda.h>
 #include "conv_tc.cuh"
@@ -43,6 +44,17 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t elect_one() {          // one lane of the (fully converged) warp
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred;
 }
 
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
@@ -85,80 +97,87 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
-        // ===== TMA producer: one thread, one tensor load per K-chunk group =====
-        if (lane == 0) {
-            const int nstages = pl.nstages, stride = pl.stride;
-            int slot = 0;
-            uint32_t ephase = 1;                                   // fresh barrier: parity 1 passes immediately
-            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
-                const TileCoord tc0 = tile_coord(t, tp);
-                const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
-                for (int s = 0; s < nstages; ++s) {
-                    const TmaStage sg = pl.st[s];
-                    mbar_wait(empty0 + 8 * slot, ephase);
-                    const uint32_t bar = full0 + 8 * slot;
-                    const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
-                    mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
-                    const uint32_t dst0 = smem_u32(sA) + slot * a_slot_bytes;
-                    for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
-                        const TmaOp op = pl.op[o];
-                        if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
-                        else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
-                    }
-                    if (!tp.resident_b)
-                        bulk_g2s(smem_u32(sB) + slot * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
-                    if (++slot == NS) { slot = 0; ephase ^= 1; }
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ===== TMA producers: three warps take the stages round-robin; warp-uniform control flow, one elected lane issues
+        // (so every operand of the tensor loads lives in uniform registers: no per-lane waterfall loops) =====
+        const int pidx = warp == 0 ? 0 : warp - 1;
+        if (warp == 2 && tp.resident_b) {                           // resident weights: one bulk-TMA burst at kernel start
+            if (elect_one()) {
+                const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
+                mbar_arrive_expect_tx(wfull, total);
+                for (uint32_t o = 0; o < total; o += 32768u) {
+                    const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
+                    bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_i8(N);
-            const int nstages = pl.nstages;
-            if (tp.resident_b) mbar_wait(wfull, 0);
-            int slot = 0, b = 0;
-            uint32_t fphase = 0, ephase = 3;                       // bit b = parity to wait for on tempty[b]
-            for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
-                mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
-                ephase ^= 1u << b;
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + (uint32_t)(b * N);
-                uint32_t accum = 0;
-                for (int s = 0; s < nstages; ++s) {
+        const int nstages = pl.nstages, stride = pl.stride;
+        int slot = 0, turn = 0;
+        uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
+        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+            const TileCoord tc0 = tile_coord(t, tp);
+            const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
+            for (int s = 0; s < nstages; ++s) {
+                if (turn == pidx) {
                     const TmaStage sg = pl.st[s];
-                    mbar_wait(full0 + 8 * slot, fphase);
-                    tc_fence_after();
+                    mbar_wait(empty0 + 8 * slot, ephase);
+                    if (elect_one()) {
+                        const uint32_t bar = full0 + 8 * slot;
+                        const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
+                        mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
+                        const uint32_t dst0 = smem_u32(sA) + slot * a_slot_bytes;
+                        for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
+                            const TmaOp op = pl.op[o];
+                            if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
+                            else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
+                        }
+                        if (!tp.resident_b)
+                            bulk_g2s(smem_u32(sB) + slot * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
+                    }
+                    __syncwarp();
+                }
+                if (++turn == 3) turn = 0;
+                if (++slot == NS) { slot = 0; ephase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+        const uint32_t idesc = make_idesc_i8(N);
+        const int nstages = pl.nstages;
+        if (tp.resident_b) mbar_wait(wfull, 0);
+        int slot = 0, b = 0;
+        uint32_t fphase = 0, ephase = 3;                           // bit b = parity to wait for on tempty[b]
+        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+            mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
+            ephase ^= 1u << b;
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)(b * N);
+            uint32_t accum = 0;
+            for (int s = 0; s < nstages; ++s) {
+                const TmaStage sg = pl.st[s];
+                mbar_wait(full0 + 8 * slot, fphase);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t abase = smem_u32(sA) + slot * a_slot_bytes;
                     const uint32_t bbase = smem_u32(sB) + (tp.resident_b ? (uint32_t)sg.chunk0 * N * 16u : slot * b_slot_bytes);
                     const int pairs = (sg.nchunks + 1) >> 1;      // an odd tail pairs with stale smem x zero weights
+                    uint32_t acc = accum;
                     for (int j = 0; j < pairs; ++j) {
                         const uint64_t ad = make_desc(abase + j * 4096, 2048, 128);
                         const uint64_t bd = make_desc(bbase + j * 2 * N * 16, N * 16, 128);
-                        mma_i8(dcol, ad, bd, idesc, accum);
-                        accum = 1;
+                        mma_i8(dcol, ad, bd, idesc, acc);
+                        acc = 1;
                     }
                     mma_commit(empty0 + 8 * slot);                // frees the smem slot when these MMAs retire
-                    if (++slot == NS) { slot = 0; fphase ^= 1; }
+                    if (s == nstages - 1) mma_commit(tfull0 + 8 * b);   // accumulator complete -> epilogue group b
                 }
-                mma_commit(tfull0 + 8 * b);                        // accumulator complete -> epilogue group b
-                b ^= 1;
+                __syncwarp();
+                accum = 1;
+                if (++slot == NS) { slot = 0; fphase ^= 1; }
             }
+            b ^= 1;
         }
-        __syncwarp();
-    } else if (warp == 2) {
-        // ===== resident weights: one bulk-TMA burst at kernel start =====
-        if (lane == 0 && tp.resident_b) {
-            const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
-            mbar_arrive_expect_tx(wfull, total);
-            for (uint32_t o = 0; o < total; o += 32768u) {
-                const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
-                bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
-            }
-        }
-        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int grp = (warp - 4) >> 2;                         // tile parity this group drains
