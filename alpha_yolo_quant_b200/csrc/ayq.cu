@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <map>
 
 #include "../../include/ayq.h"
 #include "plan_format.h"
@@ -57,7 +58,7 @@ struct ayq_engine {
     bool debug_sync = false;
     int last_n = 0;
     // host-pipeline resources
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr, s_cap = nullptr;
     float* d_img[2] = {nullptr, nullptr};
     uint8_t* d_img_u8[2] = {nullptr, nullptr};
     float* d_dets[2] = {nullptr, nullptr};
@@ -70,6 +71,8 @@ struct ayq_engine {
     std::vector<float> op_ms;
     std::vector<int> op_calls;
     std::vector<cudaEvent_t> prof_ev;
+    std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
+    bool use_graph = true;
     TcState tc;                            // tcgen05 path state
     TmaState tma;                          // TMA-fed tcgen05 path: driver entry point for tensor-map encoding
     std::vector<TmaLaunch> tma_cache;      // per op: tensor maps + stage plan for the last pass size
@@ -82,7 +85,9 @@ static inline float f_from_bits(int32_t b) { float f; memcpy(&f, &b, 4); return 
 extern "C" const char* ayq_last_error(void) { return g_err.c_str(); }
 extern "C" int ayq_version(void) { return AYQ_PLAN_VERSION; }
 
+static void drop_graphs(ayq_engine* e);
 static void free_workspace(ayq_engine* e) {
+    drop_graphs(e);
     if (e->ws) cudaFree(e->ws);
     e->ws = nullptr; e->ws_bytes = 0; e->cap = 0;
     for (auto p : e->d_kc) if (p) cudaFree(p);
@@ -200,6 +205,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
+    e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
+    g_pdl = getenv("AYQ_NO_PDL") == nullptr ? 1 : 0;
     tc_init(e->tc);
     tma_init(e->tma);
     e->op_ms.assign(h.n_ops + 1, 0.f);
@@ -225,6 +232,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    if (e->s_cap) cudaStreamDestroy(e->s_cap);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
     return 0;
@@ -238,6 +246,7 @@ extern "C" int ayq_set_max_batch(ayq_handle e, int max_batch) {
 extern "C" size_t ayq_workspace_bytes(ayq_handle e) { return e ? e->ws_bytes : 0; }
 extern "C" int ayq_set_conv_impl(ayq_handle e, int impl) {
     if (!e || impl < 0 || impl > 2) return fail(-22, "ayq_set_conv_impl: 0 (dp4a), 1 (tcgen05, cp.async feed) or 2 (tcgen05, TMA feed)");
+    if (e->conv_impl != impl) drop_graphs(e);
     e->conv_impl = impl;
     return 0;
 }
@@ -310,102 +319,154 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     const unsigned gx = (unsigned)((npix + 127) / 128);
     const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;       // the sigmoid table is only read by the SiLU epilogue
     if (a.cout % 32 == 0) {
-        conv_dp4a_kernel<32><<<dim3(gx, a.cout / 32), 128, (size_t)a.nkc * 32 * 16 + lut_bytes, st>>>(a);
+        CK(launch_k(conv_dp4a_kernel<32>, dim3(gx, a.cout / 32), dim3(128), (size_t)a.nkc * 32 * 16 + lut_bytes, st, a));
     } else {
-        conv_dp4a_kernel<16><<<dim3(gx, a.cout / 16), 128, (size_t)a.nkc * 16 * 16 + lut_bytes, st>>>(a);
+        CK(launch_k(conv_dp4a_kernel<16>, dim3(gx, a.cout / 16), dim3(128), (size_t)a.nkc * 16 * 16 + lut_bytes, st, a));
     }
     return 0;
 }
 
-static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
+struct PassArgs { const float* img; int n; float* dbox_cls; float* dets; int32_t* counts; };
+
+// launch plan op i of a pass
+static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t st) {
     const int H = e->hdr.img_h, W = e->hdr.img_w, A = e->hdr.n_anchors;
+    const int n = pa.n;
+    const float* img = pa.img;
+    float* dbox_cls = pa.dbox_cls; float* dets = pa.dets; int32_t* counts = pa.counts;
     float* amax = (float*)(e->ws + e->off_amax);
     float4* dbox = (float4*)(e->ws + e->off_dbox);
     int* conf = (int*)(e->ws + e->off_conf);
     int* cls = (int*)(e->ws + e->off_cls);
+    const int32_t* f = e->ops[i].f;
+    switch (f[0]) {
+    case OP_CONV_P1: {
+        P1Args a;
+        a.img = img; a.amax = amax;
+        a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
+        a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
+        a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
+        a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
+        P1Const pc;
+        const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
+        const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);         // [4][16]
+        const int* hb = (const int*)(e->host_data.data() + f[P1_BIAS_OFF]);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int co = 0; co < 16; ++co) {
+                const int8_t* w = hw + co * 32 + tap * 3;
+                pc.w4[tap][co] = (unsigned)(uint8_t)w[0] | ((unsigned)(uint8_t)w[1] << 8) | ((unsigned)(uint8_t)w[2] << 16);
+            }
+        for (int co = 0; co < 16; ++co) {
+            pc.k1[co] = ht[co]; pc.i1[co] = ht[16 + co]; pc.k2[co] = ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
+        }
+        CK(launch_k(conv_p1_kernel, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
+        break;
+    }
+    case OP_CONV: {
+        int rc = launch_conv(e, (int)i, n, st);
+        if (rc) return rc;
+        break;
+    }
+    case OP_POOL: {
+        const BufDesc& ib = e->bufs[f[PL_IN_BUF]];
+        const BufDesc& ob = e->bufs[f[PL_OUT_BUF]];
+        const size_t ppx = (size_t)n * f[PL_H] * f[PL_W] * 16;
+        const int8_t* in = (const int8_t*)(e->ws + e->buf_off[f[PL_IN_BUF]]) + (size_t)f[PL_IN_PLANE0] * ppx;
+        int8_t* out = (int8_t*)(e->ws + e->buf_off[f[PL_OUT_BUF]]) + (size_t)f[PL_OUT_PLANE0] * ppx;
+        (void)ib; (void)ob;
+        CK(launch_k(sppf_pool_kernel, dim3(f[PL_NPLANES], n), dim3(256), (size_t)f[PL_H] * f[PL_W] * 16 * 2, st, in, out, n, (int)f[PL_H], (int)f[PL_W], (int)f[PL_NPLANES]));
+        break;
+    }
+    case OP_HEAD: {
+        HeadArgs a;
+        for (int l = 0; l < 3; ++l) {
+            a.box[l] = (const int8_t*)(e->ws + e->buf_off[f[HD_BOX_BUF0 + l]]);
+            a.cls[l] = (const int16_t*)(e->ws + e->buf_off[f[HD_CLS_BUF0 + l]]);
+        }
+        a.lut_exp = (const float*)(e->d_data + f[HD_LUT_EXP_OFF]);
+        a.lut16 = (const int16_t*)(e->d_data + f[HD_LUT16_OFF]);
+        a.lo16 = (const int16_t*)(e->d_data + f[HD_LO16_OFF]);
+        a.mono = f[HD_MONO];
+        a.dflw = (const int*)(e->d_data + f[HD_DFLW_OFF]);
+        a.anchors = (const int*)(e->d_data + f[HD_ANCH_OFF]);
+        a.kd = f_from_bits(f[HD_KD]); a.id = f_from_bits(f[HD_ID]);
+        a.n = n; a.K = e->hdr.K; a.A = A;
+        a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.dbox_cls = dbox_cls;
+        CK(launch_k(head_kernel, dim3((unsigned)(((size_t)n * A + 127) / 128)), dim3(128), 0, st, a));
+        break;
+    }
+    case OP_NMS: {
+        NmsArgs a;
+        a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.boxes = nullptr; a.scores = nullptr; a.n = n; a.A = A; a.mode = 0; a.max_keep = NMS_MAXDET; a.dets = dets; a.counts = counts;
+        CK(launch_k(nms_kernel, dim3(n), dim3(NMS_THREADS), NMS_SMEM, st, a));
+        break;
+    }
+    default:
+        return fail(-22, "plan op %zu has unknown kind %d", i, f[0]);
+    }
+    return 0;
+}
+
+static void drop_graphs(ayq_engine* e) {
+    for (auto& kv : e->graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+}
+
+// One pass = memset + abs-max + the plan ops.  The ops between Conv_P1 and q_NMS touch only engine-owned memory, so for
+// a given pass size they are captured once into a CUDA graph (with the PDL edges) and replayed; Conv_P1 / q_NMS carry the
+// caller's pointers and are launched directly.
+static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
+    const int H = e->hdr.img_h, W = e->hdr.img_w;
+    float* amax = (float*)(e->ws + e->off_amax);
     const bool prof = e->profiling;
+    PassArgs pa{img, n, dbox_cls, dets, counts};
     int pe = 0;
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
-    absmax_kernel<<<dim3(64, n), 256, 0, st>>>(img, amax, (size_t)3 * H * W);
+    CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     if (e->debug_sync) {
         cudaError_t de = cudaStreamSynchronize(st);
         if (de == cudaSuccess) de = cudaGetLastError();
         if (de != cudaSuccess) return fail(-5, "absmax failed: %s", cudaGetErrorString(de));
     }
-    for (size_t i = 0; i < e->ops.size(); ++i) {
-        const int32_t* f = e->ops[i].f;
-        switch (f[0]) {
-        case OP_CONV_P1: {
-            P1Args a;
-            a.img = img; a.amax = amax;
-            a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
-            a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
-            a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
-            a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
-            P1Const pc;
-            const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
-            const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);         // [4][16]
-            const int* hb = (const int*)(e->host_data.data() + f[P1_BIAS_OFF]);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int co = 0; co < 16; ++co) {
-                    const int8_t* w = hw + co * 32 + tap * 3;
-                    pc.w4[tap][co] = (unsigned)(uint8_t)w[0] | ((unsigned)(uint8_t)w[1] << 8) | ((unsigned)(uint8_t)w[2] << 16);
-                }
-            for (int co = 0; co < 16; ++co) {
-                pc.k1[co] = ht[co]; pc.i1[co] = ht[16 + co]; pc.k2[co] = ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
+    const size_t nops = e->ops.size();
+    size_t g0 = 0, g1 = nops;                                      // graphable range [g0, g1)
+    while (g0 < nops && e->ops[g0].f[0] == OP_CONV_P1) ++g0;
+    while (g1 > g0 && e->ops[g1 - 1].f[0] == OP_NMS) --g1;
+    bool graphable = e->use_graph && !prof && !e->debug_sync && !dbox_cls && e->conv_impl == 2 && g1 > g0;
+    for (size_t i = g0; i < g1 && graphable; ++i)
+        if (e->ops[i].f[0] == OP_CONV_P1 || e->ops[i].f[0] == OP_NMS) graphable = false;
+    for (size_t i = 0; i < nops; ++i) {
+        if (graphable && i == g0) {
+            auto it = e->graphs.find(n);
+            if (it == e->graphs.end()) {
+                // record on an engine-owned stream (the caller's may be the legacy default stream, which cannot capture)
+                if (!e->s_cap) CK(cudaStreamCreateWithFlags(&e->s_cap, cudaStreamNonBlocking));
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(e->s_cap, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (size_t j = g0; j < g1 && rc == 0; ++j) rc = launch_op(e, j, pa, e->s_cap);
+                cudaError_t ce = cudaStreamEndCapture(e->s_cap, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(-5, "graph capture failed: %s", cudaGetErrorString(ce));
+                cudaGraphExec_t exec = nullptr;
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(-5, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+                it = e->graphs.emplace(n, exec).first;
             }
-            conv_p1_kernel<<<dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), 256, 0, st>>>(a, pc);
-            break;
+            CK(cudaGraphLaunch(it->second, st));
+            i = g1 - 1;
+            continue;
         }
-        case OP_CONV: {
-            int rc = launch_conv(e, (int)i, n, st);
-            if (rc) return rc;
-            break;
-        }
-        case OP_POOL: {
-            const BufDesc& ib = e->bufs[f[PL_IN_BUF]];
-            const BufDesc& ob = e->bufs[f[PL_OUT_BUF]];
-            const size_t ppx = (size_t)n * f[PL_H] * f[PL_W] * 16;
-            const int8_t* in = (const int8_t*)(e->ws + e->buf_off[f[PL_IN_BUF]]) + (size_t)f[PL_IN_PLANE0] * ppx;
-            int8_t* out = (int8_t*)(e->ws + e->buf_off[f[PL_OUT_BUF]]) + (size_t)f[PL_OUT_PLANE0] * ppx;
-            (void)ib; (void)ob;
-            sppf_pool_kernel<<<dim3(f[PL_NPLANES], n), 256, (size_t)f[PL_H] * f[PL_W] * 16 * 2, st>>>(in, out, n, f[PL_H], f[PL_W], f[PL_NPLANES]);
-            break;
-        }
-        case OP_HEAD: {
-            HeadArgs a;
-            for (int l = 0; l < 3; ++l) {
-                a.box[l] = (const int8_t*)(e->ws + e->buf_off[f[HD_BOX_BUF0 + l]]);
-                a.cls[l] = (const int16_t*)(e->ws + e->buf_off[f[HD_CLS_BUF0 + l]]);
-            }
-            a.lut_exp = (const float*)(e->d_data + f[HD_LUT_EXP_OFF]);
-            a.lut16 = (const int16_t*)(e->d_data + f[HD_LUT16_OFF]);
-            a.lo16 = (const int16_t*)(e->d_data + f[HD_LO16_OFF]);
-            a.mono = f[HD_MONO];
-            a.dflw = (const int*)(e->d_data + f[HD_DFLW_OFF]);
-            a.anchors = (const int*)(e->d_data + f[HD_ANCH_OFF]);
-            a.kd = f_from_bits(f[HD_KD]); a.id = f_from_bits(f[HD_ID]);
-            a.n = n; a.K = e->hdr.K; a.A = A;
-            a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.dbox_cls = dbox_cls;
-            head_kernel<<<(unsigned)(((size_t)n * A + 127) / 128), 128, 0, st>>>(a);
-            break;
-        }
-        case OP_NMS: {
-            NmsArgs a;
-            a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.boxes = nullptr; a.scores = nullptr; a.n = n; a.A = A; a.mode = 0; a.max_keep = NMS_MAXDET; a.dets = dets; a.counts = counts;
-            nms_kernel<<<n, NMS_THREADS, NMS_SMEM, st>>>(a);
-            break;
-        }
-        default:
-            return fail(-22, "plan op %zu has unknown kind %d", i, f[0]);
-        }
+        int rc = launch_op(e, i, pa, st);
+        if (rc) return rc;
         if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
         if (e->debug_sync) {
             cudaError_t de = cudaStreamSynchronize(st);
             if (de == cudaSuccess) de = cudaGetLastError();
-            if (de != cudaSuccess) return fail(-5, "op %zu (kind %d) failed: %s", i, f[0], cudaGetErrorString(de));
+            if (de != cudaSuccess) return fail(-5, "op %zu (kind %d) failed: %s", i, e->ops[i].f[0], cudaGetErrorString(de));
         }
     }
     CK(cudaGetLastError());

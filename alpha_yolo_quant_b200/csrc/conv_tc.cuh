@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
     const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
 
+    pdl_trigger();
     if (NBC == 0) {
         for (int i = tid; i < 4 * N; i += TC_THREADS) tab_s[i] = a.tab[i];
         for (int i = tid; i < N; i += TC_THREADS) bias_s[i] = a.bias[i];
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
 
     if (warp < 4) {
         // ===== producers: im2col gather, one output pixel (GEMM row) per thread =====
@@ -570,8 +572,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const KChunk* h_
             et.bias[c] = h_bias[c];
         }
     }
-    kern<<<grid, tc::TC_THREADS, smem, st>>>(a, tp, et, gt);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+    return launch_k(kern, dim3(grid), dim3(tc::TC_THREADS), smem, st, a, tp, et, gt) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
     const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
 
+    pdl_trigger();
+    // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
     if (NBC == 0) {
         for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
         for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i];
@@ -85,33 +87,36 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
-        mbar_init(wfull, 1);
+        if (!tp.resident_b) mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)tp.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 2 && tp.resident_b) {                               // resident weights: one bulk-TMA burst, still in the prologue
+        if (tid == 64) {
+            mbar_init(wfull, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
+            mbar_arrive_expect_tx(wfull, total);
+            for (uint32_t o = 0; o < total; o += 32768u) {
+                const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
+                bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
+            }
+        }
+        __syncwarp();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                                                     // activations of the previous layer are complete from here on
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ===== TMA producers: three warps take the stages round-robin; warp-uniform control flow, one elected lane issues
         // (so every operand of the tensor loads lives in uniform registers: no per-lane waterfall loops) =====
         const int pidx = warp == 0 ? 0 : warp - 1;
-        if (warp == 2 && tp.resident_b) {                           // resident weights: one bulk-TMA burst at kernel start
-            if (elect_one()) {
-                const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
-                mbar_arrive_expect_tx(wfull, total);
-                for (uint32_t o = 0; o < total; o += 32768u) {
-                    const uint32_t bytes = total - o < 32768u ? total - o : 32768u;
-                    bulk_g2s(smem_u32(sB) + o, a.w + o, bytes, wfull);
-                }
-            }
-            __syncwarp();
-        }
         const int nstages = pl.nstages, stride = pl.stride;
         int slot = 0, turn = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
@@ -407,8 +412,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
     TmaKernel kern = tma_pick(a.cout, a.epi);
-    kern<<<L.grid, tc::TMA_THREADS, L.smem, st>>>(a, L.tp, L.et, L.pl, L.maps);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+    return launch_k(kern, dim3(L.grid), dim3(tc::TMA_THREADS), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq

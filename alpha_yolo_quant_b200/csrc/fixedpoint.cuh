@@ -20,6 +20,13 @@
 
 namespace ayq {
 
+// ---- programmatic dependent launch (PDL): kernels of one pass are launched with programmatic stream serialization, so a
+// kernel's prologue (barrier init, TMEM allocation, weight / table loads) overlaps the tail of its predecessor.
+// pdl_wait() blocks until every prerequisite grid has completed and flushed; it must precede the first access to data
+// the predecessor wrote.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- generic (any clamp up to 2^23): used by the fp32 layer-library kernels ---------------------------
 __device__ __forceinline__ int rq_round(float t, float inv2s, int M) {
     int q = __float2int_rd(__fmaf_rd(t, inv2s, 0.5f));

@@ -8,8 +8,23 @@
 // The tcgen05 convolution lives in conv_tc.cuh; both share ConvArgs and the epilogue below.
 #pragma once
 #include "fixedpoint.cuh"
+#include <utility>
 
 namespace ayq {
+
+// Host launch helper: every kernel of a pass goes through here so that it can carry the programmatic-stream-serialization
+// attribute (PDL, see fixedpoint.cuh); g_pdl is switched off by AYQ_NO_PDL=1.
+static int g_pdl = 1;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 struct KChunk { long long off; int plane, dy, dx, pad_; };   // workspace byte offset of the buffer, plane, tap offset minus padding
 struct OutSpec { void* base; int mode; float k, inv; int up; };
@@ -109,12 +124,14 @@ __global__ void __launch_bounds__(128) conv_dp4a_kernel(const ConvArgs a) {
     uint4* sW = (uint4*)smem_raw;                                 // [nkc][NC] 16-byte rows
     float* lut_s = (float*)(smem_raw + (size_t)a.nkc * NC * 16);  // [256]
     const int c0 = blockIdx.y * NC;
+    pdl_trigger();
     for (int i = threadIdx.x; i < a.nkc * NC; i += 128) {
         int kc = i / NC, j = i % NC;
         sW[i] = *(const uint4*)(a.w + ((size_t)kc * a.cout + c0 + j) * 16);
     }
     if (a.epi == 0) fill_lut256(lut_s, a.lut, a.M, threadIdx.x, 128);
     __syncthreads();
+    pdl_wait();
     const size_t npix = (size_t)a.n * a.Hout * a.Wout;
     const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;
     if (p >= npix) return;
@@ -168,7 +185,9 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
     __shared__ float lut_s[AYQ_LUT256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    pdl_trigger();
     fill_lut256(lut_s, a.lut, a.M, tid, 256);
+    pdl_wait();                                                  // amax[] comes from the abs-max kernel
     // quant_matrix: a = max|x|, s = scale(a, k) = M / a evaluated by torch as reciprocal(a) * M (Tensor.__rtruediv__),
     // q = rint(fl32(clip(x) * s))   (utils/quant_matrix_torch.py:57-70, utils/scale.py:4-5).  new_clip(x, a) with
     // a = max|x| of the same image is the identity, so no clamp is needed here.
@@ -226,6 +245,8 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
 // ---- per-image abs-max --------------------------------------------------------------------------------
 // grid (blocks, n); out[] must be zeroed first.  |x| >= 0 so the float bit pattern orders like an int.
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, float* __restrict__ out, size_t per_image) {
+    pdl_trigger();
+    pdl_wait();
     const float* base = x + (size_t)blockIdx.y * per_image;
     float m = 0.f;
     const size_t nvec = per_image / 4;
@@ -261,6 +282,8 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const int8_t* __restrict
     unsigned* A = (unsigned*)smem_raw;                  // [H*W*4]
     unsigned* B = A + H * W * 4;
     const int pl = blockIdx.x, img = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
     const size_t plane_px = (size_t)n * H * W;
     const unsigned* src = (const unsigned*)(in + ((size_t)pl * plane_px + (size_t)img * H * W) * 16);
     const int nw = H * W * 4;
@@ -315,9 +338,11 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
     __shared__ float lexp[512];
     __shared__ int dflw[16];
     const int top = (1 << a.K) - 1;
+    pdl_trigger();
     for (int i = threadIdx.x; i <= top; i += 128) lexp[i] = a.lut_exp[i];
     if (threadIdx.x < 16) dflw[threadIdx.x] = a.dflw[threadIdx.x];
     __syncthreads();
+    pdl_wait();
     const int idx = blockIdx.x * 128 + threadIdx.x;
     if (idx >= a.n * a.A) return;
     const int img = idx / a.A, an = idx % a.A;
@@ -456,7 +481,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     const int img = blockIdx.x, tid = threadIdx.x, A = a.A;
     const int lane = tid & 31, wid = tid >> 5;
     const int* conf = a.mode == 0 ? a.conf + (size_t)img * A : nullptr;
+    pdl_trigger();
     if (tid < 8) sh[tid] = 0;
+    pdl_wait();
     // candidates: conf > 8192 (:299,:302,:327).  Only the 1000 best survive argsort(...)[:1000] (:260), so first find
     // the score c* of the 1000th best with a two-level histogram (score >> 9, score & 511) and sort only candidates
     // with score >= c* (all ties at c* are kept: the index inside the key decides among them, as a stable sort would).
