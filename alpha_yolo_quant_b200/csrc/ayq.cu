@@ -298,6 +298,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
         a.out[o].up = of[5];
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
+    a.half = 0.5f;
     if (e->conv_impl == 2) {
         TmaLaunch& L = e->tma_cache[opi];
         const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);

@@ -187,11 +187,13 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
 
 // fixed-point epilogue for 16 consecutive channels [c0, c0+16) of one pixel.  CT: coefficients from the constant bank
 // (c0 compile-time) or from shared memory.  acc[] = raw accumulators (bias not yet added).
-template <int EPI, bool CT>
+// FAST: the common case -- K = 8 (clamp 127), one identity output, no accumulator tap: straight-line code.
+template <int EPI, bool CT, bool FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
                                              const float* __restrict__ lut_s) {
     const int M = a.M, N = a.cout;
+    const float half = a.half;
     const size_t npix = (size_t)a.n * a.Hout * a.Wout;
     const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
     int r[16];
@@ -202,17 +204,19 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
             acc[4 * q + j] = v;
-            if (EPI == 0) r[4 * q + j] = silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
-            else if (EPI == 1) r[4 * q + j] = requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);
-            else r[4 * q + j] = requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
+            if (EPI == 0) r[4 * q + j] = FAST ? silu_q127(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, half)
+                                              : silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
+            else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127(__int2float_rn(v), cf.k1[j], cf.i1[j], half)
+                                                   : requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);
+            else r[4 * q + j] = FAST ? requant16_h(__int2float_rn(v), cf.k1[j], cf.i1[j], half) : requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
         }
     }
-    if (a.acc_tap) {
+    if (!FAST && a.acc_tap) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             a.acc_tap[(((size_t)img * N + c0 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
     }
-    if (EPI == 0) {                   // EPI_SILU
+    if (EPI == 0 && !FAST) {          // EPI_SILU, general outputs
         for (int o = 0; o < a.nout; ++o) {
             const OutSpec& os = a.out[o];
             uint32_t wd[4];
@@ -239,7 +243,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
                 *(uint4*)(pl + (p00 + W2 + 1) * 16) = v;
             }
         }
-    } else if (EPI == 1) {            // EPI_REQUANT8
+    } else if (EPI == 0 || EPI == 1) {   // one int8 plane row
         *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) =
             make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
     } else {                          // EPI_REQUANT16
@@ -386,18 +390,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tmem_ld_wait16(cur);
                     if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
                     else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }   // accumulator fully read: hand it back to the MMA warp
-                    if (valid) epilogue16_t<EPI, true>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, true, false>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             } else {
                 const int nb = N / 16;                                   // even (cout 128 / 256 / ...), checked by the host
                 for (int gch = 0; gch < nb; gch += 2) {
                     tmem_ld_wait16(accA);
                     tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
-                    if (valid) epilogue16_t<EPI, false>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, false>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                     tmem_ld_wait16(accB);
                     if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
                     else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }
-                    if (valid) epilogue16_t<EPI, false>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, false>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             }
         }

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 }
 
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
-template <int NBC, int EPI>
+template <int NBC, int EPI, bool FAST>
 __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
@@ -206,18 +206,18 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                     tmem_ld_wait16(cur);
                     if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
                     else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }   // accumulator fully read: hand it back to the MMA warp
-                    if (valid) epilogue16_t<EPI, true>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             } else {
                 const int nb = N / 16;                                   // even, checked by the host
                 for (int gch = 0; gch < nb; gch += 2) {
                     tmem_ld_wait16(accA);
                     tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
-                    if (valid) epilogue16_t<EPI, false>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                     tmem_ld_wait16(accB);
                     if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
                     else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }
-                    if (valid) epilogue16_t<EPI, false>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             }
         }
@@ -251,29 +251,39 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
 struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
-static inline TmaKernel tma_pick(int N, int epi) {
+template <bool FAST>
+static inline TmaKernel tma_pick_t(int N, int epi) {
     using namespace tc;
     if (epi == 0) {
         switch (N) {
-        case 16: return conv_tma_kernel<1, 0>;
-        case 32: return conv_tma_kernel<2, 0>;
-        case 64: return conv_tma_kernel<4, 0>;
-        case 80: return conv_tma_kernel<5, 0>;
-        default: return (N % 32 == 0) ? conv_tma_kernel<0, 0> : nullptr;
+        case 16: return conv_tma_kernel<1, 0, FAST>;
+        case 32: return conv_tma_kernel<2, 0, FAST>;
+        case 64: return conv_tma_kernel<4, 0, FAST>;
+        case 80: return conv_tma_kernel<5, 0, FAST>;
+        default: return (N % 32 == 0) ? conv_tma_kernel<0, 0, FAST> : nullptr;
         }
     }
-    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1> : (N % 32 == 0 ? conv_tma_kernel<0, 1> : nullptr);
-    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2> : (N % 32 == 0 ? conv_tma_kernel<0, 2> : nullptr);
+    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, FAST> : (N % 32 == 0 ? conv_tma_kernel<0, 1, FAST> : nullptr);
+    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, FAST> : (N % 32 == 0 ? conv_tma_kernel<0, 2, FAST> : nullptr);
     return nullptr;
+}
+static inline TmaKernel tma_pick(int N, int epi, bool fast) { return fast ? tma_pick_t<true>(N, epi) : tma_pick_t<false>(N, epi); }
+// FAST epilogue: clamp 127 (16-bit logits: 32767), a single identity output, no accumulator tap
+static inline bool tma_fast(const ConvArgs& a) {
+    if (a.acc_tap) return false;
+    if (a.epi == 2) return true;
+    if (a.M != 127) return false;
+    return a.epi == 1 || (a.nout == 1 && a.out[0].mode == 0 && !a.out[0].up);
 }
 
 static inline void tma_init(TmaState& s) {
     const int ns[] = {16, 32, 64, 80, 128};
     for (int epi = 0; epi < 3; ++epi)
-        for (int N : ns) {
-            TmaKernel k = tma_pick(N, epi);
-            if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        }
+        for (int N : ns)
+            for (int fast = 0; fast < 2; ++fast) {
+                TmaKernel k = tma_pick(N, epi, fast != 0);
+                if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -295,7 +305,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.n = a.n; L.ok = 0;
     if (!s.ready) return 0;
     const int N = a.cout;
-    if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi)) return 0;
+    if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, false)) return 0;
     tc::TcParams& tp = L.tp;
     int bw_log = 4;
     while (bw_log > 0 && (a.Wout % (1 << bw_log))) --bw_log;
@@ -411,7 +421,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 }
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
-    TmaKernel kern = tma_pick(a.cout, a.epi);
+    TmaKernel kern = tma_pick(a.cout, a.epi, tma_fast(a));
     return launch_k(kern, dim3(L.grid), dim3(tc::TMA_THREADS), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 

@@ -75,6 +75,21 @@ __device__ __forceinline__ int silu_q(int acc, float k1, float i1, float k2, flo
     const float pr = __fmul_rn(lut256[r1 + 128], a);       // res_silu *= res_conv_copy (fp32), round() is a no-op
     return max(-M, min(M, floor_sat_s8(__fmaf_rd(__fmul_rn(k2, pr), i2, 0.5f))));
 }
+// K = 8 (M = 127): the saturating conversion already bounds the result above, only -128 needs the clamp.  `half` = 0.5f
+// passed in a REGISTER (kernel parameter) so that the per-channel 2^-s can be the constant-bank operand of the FFMA.
+__device__ __forceinline__ int silu_q127(int acc, float k1, float i1, float k2, float i2,
+                                         const float* __restrict__ lut256, float half) {
+    const float a = __int2float_rn(acc);
+    const int r1 = floor_sat_s8(__fmaf_rd(__fmul_rn(k1, a), i1, half));
+    const float pr = __fmul_rn(lut256[r1 + 128], a);
+    return max(-127, floor_sat_s8(__fmaf_rd(__fmul_rn(k2, pr), i2, half)));
+}
+__device__ __forceinline__ int requant8_127(float x, float k, float inv2s, float half) {
+    return max(-127, floor_sat_s8(__fmaf_rd(__fmul_rn(k, x), inv2s, half)));
+}
+__device__ __forceinline__ int requant16_h(float x, float k, float inv2s, float half) {
+    return max(-32767, floor_sat_s16(__fmaf_rd(__fmul_rn(k, x), inv2s, half)));
+}
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
     return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);

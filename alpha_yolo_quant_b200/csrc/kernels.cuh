@@ -38,6 +38,7 @@ struct ConvArgs {
     int n, Hin, Win, Hout, Wout, stride, cout, epi, M;
     int nout; OutSpec out[3];
     int* acc_tap;               // NCHW int32 (n, cout, Hout, Wout) or nullptr
+    float half;                 // 0.5f, kept in a register by the fast epilogues (see silu_q127)
 };
 
 // ---- shared epilogue: 16 consecutive output channels [c0, c0+16) of one output pixel -----------------
