@@ -73,6 +73,8 @@ struct ayq_engine {
     std::vector<cudaEvent_t> prof_ev;
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
+    bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
+    long long* d_role = nullptr;
     TcState tc;                            // tcgen05 path state
     TmaState tma;                          // TMA-fed tcgen05 path: driver entry point for tensor-map encoding
     std::vector<TmaLaunch> tma_cache;      // per op: tensor maps + stage plan for the last pass size
@@ -206,6 +208,12 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
+    e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
+    if (e->role_prof) {
+        e->use_graph = false;
+        cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
+        cudaMemset(e->d_role, 0, sizeof(long long) * h.n_ops * 148 * 16);
+    }
     g_pdl = getenv("AYQ_NO_PDL") == nullptr ? 1 : 0;
     tc_init(e->tc);
     tma_init(e->tma);
@@ -218,6 +226,29 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
 extern "C" int ayq_destroy(ayq_handle e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
+    if (e->role_prof && e->d_role) {
+        cudaDeviceSynchronize();
+        std::vector<long long> h((size_t)e->ops.size() * 148 * 16);
+        cudaMemcpy(h.data(), e->d_role, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "role profile of the last pass (kilo-cycles, mean over CTAs): op name | prod0 total/wait | prod1 | prod2 | mma total/wait_tempty/wait_full | epi0 total/wait | epi1\n");
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            if (e->ops[i].f[0] != OP_CONV) continue;
+            double m[16] = {0};
+            int cnt = 0;
+            for (int b = 0; b < 148; ++b) {
+                const long long* r = &h[(i * 148 + b) * 16];
+                if (r[6] == 0) continue;
+                ++cnt;
+                for (int k = 0; k < 16; ++k) m[k] += (double)r[k];
+            }
+            if (!cnt) continue;
+            const char* nm = (const char*)(e->host_data.data() + e->ops[i].f[CF_NAME_OFF]);
+            fprintf(stderr, "%3zu %-20s | %6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f\n", i, nm,
+                    m[0] / cnt / 1e3, m[1] / cnt / 1e3, m[2] / cnt / 1e3, m[3] / cnt / 1e3, m[4] / cnt / 1e3, m[5] / cnt / 1e3,
+                    m[6] / cnt / 1e3, m[7] / cnt / 1e3, m[8] / cnt / 1e3, m[9] / cnt / 1e3, m[10] / cnt / 1e3, m[11] / cnt / 1e3, m[12] / cnt / 1e3);
+        }
+        cudaFree(e->d_role);
+    }
     free_workspace(e);
     if (e->d_data) cudaFree(e->d_data);
     for (int i = 0; i < 2; ++i) {
@@ -299,6 +330,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
     a.half = 0.5f;
+    a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * 16 : nullptr;
     if (e->conv_impl == 2) {
         TmaLaunch& L = e->tma_cache[opi];
         const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);

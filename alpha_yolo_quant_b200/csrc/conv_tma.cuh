@@ -120,13 +120,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         const int nstages = pl.nstages, stride = pl.stride;
         int slot = 0, turn = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
+        long long d_wait = 0, d_t0 = a.dbg ? clock64() : 0;
         for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
             for (int s = 0; s < nstages; ++s) {
                 if (turn == pidx) {
                     const TmaStage sg = pl.st[s];
+                    const long long w0 = a.dbg ? clock64() : 0;
                     mbar_wait(empty0 + 8 * slot, ephase);
+                    if (a.dbg) d_wait += clock64() - w0;
                     if (elect_one()) {
                         const uint32_t bar = full0 + 8 * slot;
                         const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                 if (++slot == NS) { slot = 0; ephase ^= 1; }
             }
         }
+        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + pidx * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + pidx * 2 + 1] = d_wait; }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
         const uint32_t idesc = make_idesc_i8(N);
@@ -153,15 +157,20 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         if (tp.resident_b) mbar_wait(wfull, 0);
         int slot = 0, b = 0;
         uint32_t fphase = 0, ephase = 3;                           // bit b = parity to wait for on tempty[b]
+        long long d_we = 0, d_wf = 0, d_t0 = a.dbg ? clock64() : 0;
         for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+            const long long w0 = a.dbg ? clock64() : 0;
             mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
+            if (a.dbg) d_we += clock64() - w0;
             ephase ^= 1u << b;
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)(b * N);
             uint32_t accum = 0;
             for (int s = 0; s < nstages; ++s) {
                 const TmaStage sg = pl.st[s];
+                const long long w1 = a.dbg ? clock64() : 0;
                 mbar_wait(full0 + 8 * slot, fphase);
+                if (a.dbg) d_wf += clock64() - w1;
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t abase = smem_u32(sA) + slot * a_slot_bytes;
@@ -183,6 +192,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
             }
             b ^= 1;
         }
+        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7] = d_we; a.dbg[blockIdx.x * 16 + 8] = d_wf; }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int grp = (warp - 4) >> 2;                         // tile parity this group drains
@@ -190,11 +200,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * N);
         uint32_t tphase = 0;
+        long long d_wt = 0, d_t0 = a.dbg ? clock64() : 0;
         for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x, tphase ^= 1) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
+            const long long w0 = a.dbg ? clock64() : 0;
             mbar_wait(tfull0 + 8 * grp, tphase);
+            if (a.dbg) d_wt += clock64() - w0;
             tc_fence_after();
             int accA[16], accB[16];
             tmem_ld16(lane_base, accA);
@@ -221,6 +234,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                 }
             }
         }
+        if (a.dbg && (warp & 3) == 0 && lane == 0) { a.dbg[blockIdx.x * 16 + 9 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 10 + 2 * grp] = d_wt; }
     }
     tc_fence_before();
     __syncthreads();
@@ -320,7 +334,9 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     if ((unsigned long long)tp.ntiles * (unsigned)tp.tiles_x >= (1ull << 32)) return 0;
     if ((1 << bw_log) * a.stride > 256 || (1 << bh_log) * a.stride > 256 || bn > 256) return 0;
     tp.nkc_pad = (a.nkc + 1) & ~1;
-    const int slot_chunks = N <= 64 ? 16 : 8;                    // 32 KB / 16 KB of A per ring slot
+    // ring slot = 32 KB / 16 KB of A, or the whole (small) K extent: small slots leave room for a deep ring
+    const int slot_cap = N <= 64 ? 16 : 8;
+    const int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
     tp.KS = slot_chunks; tp.nst = 0; tp.lag = 0;
     int cols = 32;
     while (cols < 2 * N) cols <<= 1;
@@ -405,7 +421,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const size_t per_slot = (size_t)slot_chunks * 2048 + (tp.resident_b ? 0 : (size_t)slot_chunks * N * 16);
     const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
     int ns = (int)(avail / per_slot);
-    if (ns > 8) ns = 8;
+    if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
     if (ns < 2) return 0;
     tp.NS = ns;
     L.smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_slot;

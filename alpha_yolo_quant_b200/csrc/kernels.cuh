@@ -39,6 +39,7 @@ struct ConvArgs {
     int nout; OutSpec out[3];
     int* acc_tap;               // NCHW int32 (n, cout, Hout, Wout) or nullptr
     float half;                 // 0.5f, kept in a register by the fast epilogues (see silu_q127)
+    long long* dbg;             // AYQ_ROLE_PROF=1: per-CTA cycle counters of the warp roles [grid][16], else nullptr
 };
 
 // ---- shared epilogue: 16 consecutive output channels [c0, c0+16) of one output pixel -----------------
