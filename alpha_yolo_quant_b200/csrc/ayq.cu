@@ -230,7 +230,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
         cudaDeviceSynchronize();
         std::vector<long long> h((size_t)e->ops.size() * 148 * 16);
         cudaMemcpy(h.data(), e->d_role, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "role profile of the last pass (kilo-cycles, mean over CTAs): op name | prod0 total/wait | prod1 | prod2 | mma total/wait_tempty/wait_full | epi0 total/wait | epi1\n");
+        fprintf(stderr, "role profile of the last pass (kilo-cycles, mean over CTAs): op name | prod0 total/wait_empty | prod1 | mma0 total/wait_tempty/wait_full | mma1 | epi0 total/wait_tfull | epi1\n");
         for (size_t i = 0; i < e->ops.size(); ++i) {
             if (e->ops[i].f[0] != OP_CONV) continue;
             double m[16] = {0};
@@ -243,9 +243,10 @@ extern "C" int ayq_destroy(ayq_handle e) {
             }
             if (!cnt) continue;
             const char* nm = (const char*)(e->host_data.data() + e->ops[i].f[CF_NAME_OFF]);
-            fprintf(stderr, "%3zu %-20s | %6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f\n", i, nm,
-                    m[0] / cnt / 1e3, m[1] / cnt / 1e3, m[2] / cnt / 1e3, m[3] / cnt / 1e3, m[4] / cnt / 1e3, m[5] / cnt / 1e3,
-                    m[6] / cnt / 1e3, m[7] / cnt / 1e3, m[8] / cnt / 1e3, m[9] / cnt / 1e3, m[10] / cnt / 1e3, m[11] / cnt / 1e3, m[12] / cnt / 1e3);
+            fprintf(stderr, "%3zu %-20s | %6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f/%6.1f | %6.1f/%6.1f/%6.1f | %6.1f/%6.1f | %6.1f/%6.1f\n", i, nm,
+                    m[0] / cnt / 1e3, m[1] / cnt / 1e3, m[2] / cnt / 1e3, m[3] / cnt / 1e3,
+                    m[6] / cnt / 1e3, m[7] / cnt / 1e3, m[8] / cnt / 1e3, m[9] / cnt / 1e3, m[10] / cnt / 1e3, m[11] / cnt / 1e3,
+                    m[12] / cnt / 1e3, m[13] / cnt / 1e3, m[14] / cnt / 1e3, m[15] / cnt / 1e3);
         }
         cudaFree(e->d_role);
     }

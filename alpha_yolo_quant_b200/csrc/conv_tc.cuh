@@ -104,6 +104,19 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// same MMA with the two 64-bit shared-memory descriptors given as (lo, hi) halves: the loops keep `lo` (address | LBO) in a
+// register and step it by plain 32-bit adds, `hi` (SBO | version) is loop invariant
+__device__ __forceinline__ void mma_i8_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 ad, bd;\n\t"
+        "mov.b64 ad, {%1, %2};\n\t"
+        "mov.b64 bd, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %5, {%7, %7, %7, %7}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -10,8 +10,9 @@
 //   * the convolution stride is the TMA element stride;
 //   * concat / residual-sum inputs are further groups from other tensor maps (plan.py's segment lists).
 // One elected thread issues the loads (no producer warps, no per-pixel address arithmetic, no proxy fences); stages are
-// packed on the host from whole boxes.  Warp roles: warps 0, 2, 3 = TMA producers (stages round-robin;
-// A, and B when the weights are streamed; warp 2 also loads resident weights), warp 1 = MMA issuer + TMEM allocator,
+// packed on the host from whole boxes.  Warp roles: warps 2, 3 = TMA producers (stages round-robin;
+// A, and B when the weights are streamed; warp 2 also loads resident weights), warps 0, 1 = MMA issuers (even / odd tiles;
+// warp 1 also owns the TMEM allocation),
 // warps 4-7 / 8-11 = epilogue of even / odd tiles.
 #pragma once
 #include <cuda.h>
@@ -113,86 +114,99 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     const uint32_t tmem_base = tmem_base_s;
     pdl_wait();                                                     // activations of the previous layer are complete from here on
 
-    if (warp == 0 || warp == 2 || warp == 3) {
-        // ===== TMA producers: three warps take the stages round-robin; warp-uniform control flow, one elected lane issues
-        // (so every operand of the tensor loads lives in uniform registers: no per-lane waterfall loops) =====
-        const int pidx = warp == 0 ? 0 : warp - 1;
+    // Two independent pipelines share the CTA: pipeline m (m = 0, 1) = producer warp 2+m -> ring slots [m*NSH, (m+1)*NSH) ->
+    // MMA issuer warp m -> TMEM buffer m -> epilogue group m, and handles the tiles i with i % 2 == m.  A single issuer's
+    // per-tile loop (barrier probes, fences, elect, descriptor moves to uniform registers, MMAs, commits) is a serial chain
+    // of several hundred cycles; two pipelines overlap their chains, and private rings keep every barrier strictly in-order
+    // for its one producer / one consumer (parity waits cannot alias).
+    const int NSH = NS >> 1;
+    if (warp == 2 || warp == 3) {
+        // ===== TMA producer of pipeline m: warp-uniform control flow, one elected lane issues (all operands of the tensor
+        // loads live in uniform registers: no per-lane waterfall loops) =====
+        const int m = warp - 2;
         const int nstages = pl.nstages, stride = pl.stride;
-        int slot = 0, turn = 0;
+        const int slot0 = m * NSH;
+        int slot = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
         long long d_wait = 0, d_t0 = a.dbg ? clock64() : 0;
-        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+        for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
             for (int s = 0; s < nstages; ++s) {
-                if (turn == pidx) {
-                    const TmaStage sg = pl.st[s];
-                    const long long w0 = a.dbg ? clock64() : 0;
-                    mbar_wait(empty0 + 8 * slot, ephase);
-                    if (a.dbg) d_wait += clock64() - w0;
-                    if (elect_one()) {
-                        const uint32_t bar = full0 + 8 * slot;
-                        const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
-                        mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
-                        const uint32_t dst0 = smem_u32(sA) + slot * a_slot_bytes;
-                        for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
-                            const TmaOp op = pl.op[o];
-                            if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
-                            else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
-                        }
-                        if (!tp.resident_b)
-                            bulk_g2s(smem_u32(sB) + slot * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
+                const TmaStage sg = pl.st[s];
+                const int gs = slot0 + slot;
+                const long long w0 = a.dbg ? clock64() : 0;
+                mbar_wait(empty0 + 8 * gs, ephase);
+                if (a.dbg) d_wait += clock64() - w0;
+                if (elect_one()) {
+                    const uint32_t bar = full0 + 8 * gs;
+                    const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
+                    mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
+                    const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
+                    for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
+                        const TmaOp op = pl.op[o];
+                        if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
+                        else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
                     }
-                    __syncwarp();
+                    if (!tp.resident_b)
+                        bulk_g2s(smem_u32(sB) + gs * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
                 }
-                if (++turn == 3) turn = 0;
-                if (++slot == NS) { slot = 0; ephase ^= 1; }
+                __syncwarp();
+                if (++slot == NSH) { slot = 0; ephase ^= 1; }
             }
         }
-        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + pidx * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + pidx * 2 + 1] = d_wait; }
-    } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
+    } else if (warp < 2) {
+        // ===== MMA issuer of pipeline m: warp-uniform control flow, one elected lane issues; the descriptor low words
+        // (address | LBO) are stepped with 32-bit adds =====
+        const int m = warp;
         const uint32_t idesc = make_idesc_i8(N);
         const int nstages = pl.nstages;
         if (tp.resident_b) mbar_wait(wfull, 0);
-        int slot = 0, b = 0;
-        uint32_t fphase = 0, ephase = 3;                           // bit b = parity to wait for on tempty[b]
+        const uint32_t d_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1 (bits 32.. of make_desc)
+        const uint32_t a_lo0 = ((smem_u32(sA) & 0x3ffffu) >> 4) | ((2048u >> 4) << 16);
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3ffffu) >> 4) | ((((uint32_t)N * 16u) >> 4) << 16);
+        const uint32_t a_step = a_slot_bytes >> 4, b_step = tp.resident_b ? 0u : (b_slot_bytes >> 4);
+        const uint32_t b_pair = 2u * (uint32_t)N;                  // two K chunks of B, in 16-byte units
+        const TmaStage sg0 = pl.st[0];
+        const uint32_t dcol = tmem_base + (uint32_t)(m * N);
+        const int slot0 = m * NSH;
+        int slot = 0;
+        uint32_t fphase = 0, ephase = 1;                           // fresh tempty barrier: parity 1 passes immediately
         long long d_we = 0, d_wf = 0, d_t0 = a.dbg ? clock64() : 0;
-        for (int t = blockIdx.x; t < tp.ntiles; t += gridDim.x) {
+        for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const long long w0 = a.dbg ? clock64() : 0;
-            mbar_wait(tempty0 + 8 * b, (ephase >> b) & 1u);
+            mbar_wait(tempty0 + 8 * m, ephase);
             if (a.dbg) d_we += clock64() - w0;
-            ephase ^= 1u << b;
+            ephase ^= 1;
             tc_fence_after();
-            const uint32_t dcol = tmem_base + (uint32_t)(b * N);
             uint32_t accum = 0;
             for (int s = 0; s < nstages; ++s) {
-                const TmaStage sg = pl.st[s];
+                TmaStage sg = sg0;
+                if (s > 0) sg = pl.st[s];
+                const int gs = slot0 + slot;
                 const long long w1 = a.dbg ? clock64() : 0;
-                mbar_wait(full0 + 8 * slot, fphase);
+                mbar_wait(full0 + 8 * gs, fphase);
                 if (a.dbg) d_wf += clock64() - w1;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t abase = smem_u32(sA) + slot * a_slot_bytes;
-                    const uint32_t bbase = smem_u32(sB) + (tp.resident_b ? (uint32_t)sg.chunk0 * N * 16u : slot * b_slot_bytes);
+                    uint32_t alo = a_lo0 + (uint32_t)gs * a_step;
+                    uint32_t blo = tp.resident_b ? b_lo0 + (uint32_t)sg.chunk0 * (uint32_t)N : b_lo0 + (uint32_t)gs * b_step;
                     const int pairs = (sg.nchunks + 1) >> 1;      // an odd tail pairs with stale smem x zero weights
                     uint32_t acc = accum;
                     for (int j = 0; j < pairs; ++j) {
-                        const uint64_t ad = make_desc(abase + j * 4096, 2048, 128);
-                        const uint64_t bd = make_desc(bbase + j * 2 * N * 16, N * 16, 128);
-                        mma_i8(dcol, ad, bd, idesc, acc);
-                        acc = 1;
+                        mma_i8_lh(dcol, alo, d_hi, blo, d_hi, idesc, acc);
+                        acc = 1; alo += 256u; blo += b_pair;
                     }
-                    mma_commit(empty0 + 8 * slot);                // frees the smem slot when these MMAs retire
-                    if (s == nstages - 1) mma_commit(tfull0 + 8 * b);   // accumulator complete -> epilogue group b
+                    mma_commit(empty0 + 8 * gs);                  // frees the smem slot when these MMAs retire
+                    if (s == nstages - 1) mma_commit(tfull0 + 8 * m);   // accumulator complete -> epilogue group m
                 }
                 __syncwarp();
                 accum = 1;
-                if (++slot == NS) { slot = 0; fphase ^= 1; }
+                if (++slot == NSH) { slot = 0; fphase ^= 1; }
             }
-            b ^= 1;
         }
-        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7] = d_we; a.dbg[blockIdx.x * 16 + 8] = d_wf; }
+        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int grp = (warp - 4) >> 2;                         // tile parity this group drains
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                 }
             }
         }
-        if (a.dbg && (warp & 3) == 0 && lane == 0) { a.dbg[blockIdx.x * 16 + 9 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 10 + 2 * grp] = d_wt; }
+        if (a.dbg && (warp & 3) == 0 && lane == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
     }
     tc_fence_before();
     __syncthreads();
@@ -422,7 +436,8 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
     int ns = (int)(avail / per_slot);
     if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
-    if (ns < 2) return 0;
+    ns &= ~1;                                                     // two pipelines, each with a private ring of ns / 2 slots
+    if (ns < 4) return 0;
     tp.NS = ns;
     L.smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_slot;
     L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
