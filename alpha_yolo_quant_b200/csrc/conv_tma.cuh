@@ -25,7 +25,7 @@ namespace tc {
 constexpr int TMA_MAX_MAPS = 8;
 constexpr int TMA_MAX_OPS = 56;
 constexpr int TMA_MAX_STAGES = 24;
-constexpr int TMA_THREADS = 384;
+constexpr int TMA_THREADS = 512;                 // warps 0-1 MMA issuers, 2-5 TMA producers, 6-7 idle, 8-15 epilogue
 
 struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box origin offsets (tap - pad), first plane, byte offset in the slot
 struct TmaStage { int op0, nops, nchunks, chunk0; };
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 5];   // full[NS], empty[NS], tfull[2], tempty[2], wfull
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 9];   // full[NS], empty[NS], tfull[4], tempty[4], wfull
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.cout, NS = tp.NS;
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     int* bias_s = (int*)(tab_s + 4 * N);
     float* lut_s = (float*)(bias_s + N);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 4]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 8]);
+    const int nbuf = tp.tmem_cols >= 4 * N ? 2 : 1;               // TMEM accumulator buffers per pipeline (cout 256: one)
 
     pdl_trigger();
     // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
         if (!tp.resident_b) mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -120,42 +121,46 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     // of several hundred cycles; two pipelines overlap their chains, and private rings keep every barrier strictly in-order
     // for its one producer / one consumer (parity waits cannot alias).
     const int NSH = NS >> 1;
-    if (warp == 2 || warp == 3) {
-        // ===== TMA producer of pipeline m: warp-uniform control flow, one elected lane issues (all operands of the tensor
-        // loads live in uniform registers: no per-lane waterfall loops) =====
-        const int m = warp - 2;
+    if (warp >= 2 && warp < 6) {
+        // ===== TMA producers of pipeline m (two warps per pipeline, q = 0 / 1 take the even / odd stages of its ring; NSH is
+        // even, so a slot always belongs to the same producer): warp-uniform control flow, one elected lane issues (all
+        // operands of the tensor loads live in uniform registers: no per-lane waterfall loops) =====
+        const int m = (warp - 2) & 1, q = (warp - 2) >> 1;
         const int nstages = pl.nstages, stride = pl.stride;
         const int slot0 = m * NSH;
-        int slot = 0;
+        int slot = 0, turn = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
         long long d_wait = 0, d_t0 = a.dbg ? clock64() : 0;
         for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
             for (int s = 0; s < nstages; ++s) {
-                const TmaStage sg = pl.st[s];
-                const int gs = slot0 + slot;
-                const long long w0 = a.dbg ? clock64() : 0;
-                mbar_wait(empty0 + 8 * gs, ephase);
-                if (a.dbg) d_wait += clock64() - w0;
-                if (elect_one()) {
-                    const uint32_t bar = full0 + 8 * gs;
-                    const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
-                    mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
-                    const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
-                    for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
-                        const TmaOp op = pl.op[o];
-                        if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
-                        else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
+                if (turn == q) {
+                    const TmaStage sg = pl.st[s];
+                    const int gs = slot0 + slot;
+                    const long long w0 = a.dbg ? clock64() : 0;
+                    mbar_wait(empty0 + 8 * gs, ephase);
+                    if (a.dbg) d_wait += clock64() - w0;
+                    if (elect_one()) {
+                        const uint32_t bar = full0 + 8 * gs;
+                        const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
+                        mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
+                        const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
+                        for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
+                            const TmaOp op = pl.op[o];
+                            if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
+                            else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
+                        }
+                        if (!tp.resident_b)
+                            bulk_g2s(smem_u32(sB) + gs * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
                     }
-                    if (!tp.resident_b)
-                        bulk_g2s(smem_u32(sB) + gs * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
+                    __syncwarp();
                 }
-                __syncwarp();
+                turn ^= 1;
                 if (++slot == NSH) { slot = 0; ephase ^= 1; }
             }
         }
-        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
+        if (a.dbg && lane == 0 && q == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
     } else if (warp < 2) {
         // ===== MMA issuer of pipeline m: warp-uniform control flow, one elected lane issues; the descriptor low words
         // (address | LBO) are stepped with 32-bit adds =====
@@ -169,17 +174,17 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         const uint32_t a_step = a_slot_bytes >> 4, b_step = tp.resident_b ? 0u : (b_slot_bytes >> 4);
         const uint32_t b_pair = 2u * (uint32_t)N;                  // two K chunks of B, in 16-byte units
         const TmaStage sg0 = pl.st[0];
-        const uint32_t dcol = tmem_base + (uint32_t)(m * N);
         const int slot0 = m * NSH;
-        int slot = 0;
-        uint32_t fphase = 0, ephase = 1;                           // fresh tempty barrier: parity 1 passes immediately
+        int slot = 0, buf = 0;
+        uint32_t fphase = 0, ephase = 3;                           // bit buf = parity to wait for on tempty[m][buf]; fresh barriers pass parity 1
         long long d_we = 0, d_wf = 0, d_t0 = a.dbg ? clock64() : 0;
         for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const long long w0 = a.dbg ? clock64() : 0;
-            mbar_wait(tempty0 + 8 * m, ephase);
+            mbar_wait(tempty0 + 8 * (2 * m + buf), (ephase >> buf) & 1u);
             if (a.dbg) d_we += clock64() - w0;
-            ephase ^= 1;
+            ephase ^= 1u << buf;
             tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)((m * nbuf + buf) * N);
             uint32_t accum = 0;
             for (int s = 0; s < nstages; ++s) {
                 TmaStage sg = sg0;
@@ -199,28 +204,33 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                         acc = 1; alo += 256u; blo += b_pair;
                     }
                     mma_commit(empty0 + 8 * gs);                  // frees the smem slot when these MMAs retire
-                    if (s == nstages - 1) mma_commit(tfull0 + 8 * m);   // accumulator complete -> epilogue group m
+                    if (s == nstages - 1) mma_commit(tfull0 + 8 * (2 * m + buf));   // accumulator complete -> epilogue group m
                 }
                 __syncwarp();
                 accum = 1;
                 if (++slot == NSH) { slot = 0; fphase ^= 1; }
             }
+            if (nbuf == 2) buf ^= 1;
         }
         if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
-    } else if (warp >= 4) {
+    } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
-        const int grp = (warp - 4) >> 2;                         // tile parity this group drains
+        const int grp = (warp - 8) >> 2;                         // pipeline (tile parity) this group drains
         const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * N);
-        uint32_t tphase = 0;
+        const uint32_t lane_quad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t tphase = 0;                                     // bit buf = parity to wait for on tfull[grp][buf]
+        int buf = 0;
         long long d_wt = 0, d_t0 = a.dbg ? clock64() : 0;
-        for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x, tphase ^= 1) {
+        for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
+            const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
+            const uint32_t tfull_b = tfull0 + 8 * (2 * grp + buf), tempty_b = tempty0 + 8 * (2 * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
             const long long w0 = a.dbg ? clock64() : 0;
-            mbar_wait(tfull0 + 8 * grp, tphase);
+            mbar_wait(tfull_b, (tphase >> buf) & 1u);
+            tphase ^= 1u << buf;
             if (a.dbg) d_wt += clock64() - w0;
             tc_fence_after();
             int accA[16], accB[16];
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                     int* nxt = (gch & 1) ? accA : accB;
                     tmem_ld_wait16(cur);
                     if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
-                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }   // accumulator fully read: hand it back to the MMA warp
+                    else { tc_fence_before(); mbar_arrive(tempty_b); }   // accumulator fully read: hand it back to the MMA warp
                     if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             } else {
@@ -243,10 +253,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                     if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
                     tmem_ld_wait16(accB);
                     if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
-                    else { tc_fence_before(); mbar_arrive(tempty0 + 8 * grp); }
+                    else { tc_fence_before(); mbar_arrive(tempty_b); }
                     if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             }
+            if (nbuf == 2) buf ^= 1;
         }
         if (a.dbg && (warp & 3) == 0 && lane == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
     }
@@ -353,7 +364,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
     tp.KS = slot_chunks; tp.nst = 0; tp.lag = 0;
     int cols = 32;
-    while (cols < 2 * N) cols <<= 1;
+    while (cols < (4 * N <= 512 ? 4 : 2) * N) cols <<= 1;        // two pipelines x two accumulator buffers (one for cout 256)
     tp.tmem_cols = cols;
 
     // groups -> boxes (power-of-two plane counts, so that a stage never ends on an odd chunk before the tile's last stage)
@@ -436,7 +447,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
     int ns = (int)(avail / per_slot);
     if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
-    ns &= ~1;                                                     // two pipelines, each with a private ring of ns / 2 slots
+    ns &= ~3;                                                     // two pipelines, each with a private ring of ns / 2 slots (even: two producers)
     if (ns < 4) return 0;
     tp.NS = ns;
     L.smem = fixed + (tp.resident_b ? w_bytes : 0) + (size_t)ns * per_slot;
