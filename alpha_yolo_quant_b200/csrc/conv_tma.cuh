@@ -25,7 +25,7 @@ namespace tc {
 constexpr int TMA_MAX_MAPS = 8;
 constexpr int TMA_MAX_OPS = 56;
 constexpr int TMA_MAX_STAGES = 24;
-constexpr int TMA_THREADS = 512;                 // warps 0-1 MMA issuers, 2-5 TMA producers, 6-7 idle, 8-15 epilogue
+// block = 256 + 256 * EG threads: warps 0-1 MMA issuers, 2-5 TMA producers, 6-7 idle, then EG epilogue groups (4 warps) per pipeline
 
 struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box origin offsets (tap - pad), first plane, byte offset in the slot
 struct TmaStage { int op0, nops, nchunks, chunk0; };
@@ -59,10 +59,13 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 }
 
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
-template <int NBC, int EPI, bool FAST>
-__global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
+// EG = epilogue groups per pipeline: 2 (one group per TMEM buffer) for cout <= 32, where the epilogue is the issue-bound
+// stage and the kernels are small enough in registers for 768 threads; 1 otherwise (the group alternates buffers).
+template <int NBC, int EPI, bool FAST, int EG = ((NBC == 1 || NBC == 2) ? 2 : 1)>
+__global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
+    constexpr int TMA_THREADS = 256 + 256 * EG;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 9];   // full[NS], empty[NS], tfull[4], tempty[4], wfull
     __shared__ uint32_t tmem_base_s;
@@ -215,14 +218,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
-        const int grp = (warp - 8) >> 2;                         // pipeline (tile parity) this group drains
+        const int gq = (warp - 8) >> 2;
+        const int grp = EG == 2 ? (gq >> 1) : gq;                // pipeline (tile parity) this group drains
+        const int tstep = EG == 2 ? 4 : 2;                       // EG == 2: group (grp, gq & 1) owns TMEM buffer gq & 1, every other tile of the pipeline
         const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
         const uint32_t lane_quad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tphase = 0;                                     // bit buf = parity to wait for on tfull[grp][buf]
-        int buf = 0;
+        int buf = EG == 2 ? (gq & 1) : 0;
         long long d_wt = 0, d_t0 = a.dbg ? clock64() : 0;
-        for (int t = blockIdx.x + grp * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
+        for (int t = blockIdx.x + (grp + 2 * (EG == 2 ? (gq & 1) : 0)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
             const uint32_t tfull_b = tfull0 + 8 * (2 * grp + buf), tempty_b = tempty0 + 8 * (2 * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
@@ -257,9 +262,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
                     if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
                 }
             }
-            if (nbuf == 2) buf ^= 1;
+            if (EG == 1 && nbuf == 2) buf ^= 1;
         }
-        if (a.dbg && (warp & 3) == 0 && lane == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
+        if (a.dbg && (warp & 3) == 0 && lane == 0 && gq < 2) { a.dbg[blockIdx.x * 16 + 12 + 2 * gq] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * gq] = d_wt; }
     }
     tc_fence_before();
     __syncthreads();
@@ -464,7 +469,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
     TmaKernel kern = tma_pick(a.cout, a.epi, tma_fast(a));
-    return launch_k(kern, dim3(L.grid), dim3(tc::TMA_THREADS), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
+    return launch_k(kern, dim3(L.grid), dim3(a.cout <= 32 ? 768 : 512), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq
