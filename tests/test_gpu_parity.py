@@ -258,3 +258,24 @@ def test_nms_entry_points(golden_dir):
         order = rest[inter <= ((areas[i] + areas[rest]).astype(F) - inter).astype(F)]
     assert keep.tolist() == [int(v) for v in exp]
     e.close()
+
+
+def test_calibration_save_max_a():
+    """save_max_a (utils/save_a.py:11-26) on CUDA tap tensors: batch-1 calls like the reference and one batched call."""
+    from alpha_yolo_quant_b200 import calibration as cal
+    rng = np.random.default_rng(3)
+    taps = {'conv_p2': (4, 16, 40, 40), 'conv8': (4, 64, 10, 10)}
+    ref, one, batched = {}, {}, {}
+    for name, shp in taps.items():
+        x = (rng.standard_normal(shp) * 3).astype(np.float32)
+        x[2, 1, 3, 3] = -41.5
+        xd = torch.from_numpy(x).cuda()
+        for i in range(shp[0]):
+            cal.save_max_a(one, xd[i:i + 1], name)
+            ref.setdefault(name, []).append(float(np.abs(x[i]).max()))
+        cal.save_max_a(batched, xd, name)
+    for name in taps:
+        assert [float(v) for v in one[name]] == ref[name]
+        assert [float(v) for v in batched[name]] == ref[name]
+    txt = cal.format_max_a_all(one)
+    assert cal.parse_max_a_all(txt)['conv8'] == [round(v, 4) for v in ref['conv8']]
