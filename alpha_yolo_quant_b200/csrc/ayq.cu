@@ -54,7 +54,7 @@ struct ayq_engine {
     std::vector<std::vector<KChunk>> h_kc; // per op (host copy)
     std::vector<int*> acc_taps;            // per tap device buffers (cap images)
     std::vector<size_t> acc_tap_elems;     // per image
-    int conv_impl = 0;
+    int conv_impl = 2;                     // 2 = TMA-fed tcgen05 (falls back per layer to 1 = cp.async-fed tcgen05, then 0 = dp4a)
     bool debug_sync = false;
     int last_n = 0;
     // host-pipeline resources

@@ -118,8 +118,16 @@ class CpuReference:
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
         self.workers = workers or min(os.cpu_count() or 1, 32)     # bounded: each worker holds ~0.5 GB of im2col scratch
+        saved = {k: os.environ.get(k) for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS')}
+        for k in saved:                                            # the workers are the parallelism: one BLAS thread each
+            os.environ[k] = '1'                                    # (must be in the environment BEFORE the children import numpy)
         self.pool = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context('spawn'), initializer=_oracle_init)
         list(self.pool.map(_oracle_run, range(self.workers)))          # start every worker, build its LUTs, warm caches
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
     def rate(self, n_images, seed0=100):
         t0 = time.perf_counter()
@@ -168,7 +176,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
     ap.add_argument('--max-batch', type=int, default=128, help='images per internal pass of the engine')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--conv', default=os.environ.get('AYQ_CONV', 'tcgen05'), choices=['dp4a', 'tcgen05', 'tma'])
+    ap.add_argument('--conv', default=os.environ.get('AYQ_CONV', 'tma'), choices=['dp4a', 'tcgen05', 'tma'])
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU-baseline sample (images)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -255,10 +263,13 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             res[name] = B * world * args.steps / float(tt.item())
             assert int(counts_h.sum().item()) == n_det
-        e2e = {'value': res['f32'], 'unit': 'images/s', 'h2d_bytes_per_step': int(host_f32.numel() * 4),
+        # Headline: uint8 host images, the format the reference's validation loader holds before ToTensor
+        # (stage_8_torch.py:985-990, 1004-1013): H2D of the uint8 batch, ToTensor + forward + q_NMS on the GPU, D2H of the
+        # detections, all inside the timed C call.  The fp32-host-input variant (4x the PCIe bytes) is reported beside it.
+        e2e = {'value': res['u8'], 'unit': 'images/s', 'h2d_bytes_per_step': int(host_u8.numel()),
                'd2h_bytes_per_step': int(dets_h.numel() * 4 + counts_h.numel() * 4),
-               'input': 'float32 (B,3,640,640) pinned host, the reference forward() input format',
-               'u8_input_value': res['u8'], 'u8_h2d_bytes_per_step': int(host_u8.numel())}
+               'input': 'uint8 (B,3,640,640) pinned host -> ayq_forward_host_u8 (ToTensor on the GPU)',
+               'f32_input_value': res['f32'], 'f32_h2d_bytes_per_step': int(host_f32.numel() * 4)}
 
     # ---- per-op device times (CUDA events around every kernel, outside the timed region) -> roofline of the dominant kernel
     roofline, top = None, None
@@ -299,8 +310,13 @@ def main():
             mac = sum(r['macs_per_img'] for r in conv_rows) * imgs
             gbs = 1e-6 * byt / t_ms
             kname = {'tcgen05': 'conv_tc_kernel', 'tma': 'conv_tma_kernel'}.get(args.conv, 'conv_dp4a_kernel')
+            traffic = None
+            tp_path = os.path.join(REPO, 'profiles', 'traffic_r1.json')
+            if args.conv == 'tma' and os.path.exists(tp_path):          # DRAM bytes per launch from the committed ncu --set full capture
+                tj = json.load(open(tp_path))
+                traffic = tj['dram_bytes_per_launch'] * imgs / tj['images_per_pass']
             roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
-                        'traffic': None, 'kernel': kname, 'launches_per_pass': len(conv_rows),
+                        'traffic': traffic, 'kernel': kname, 'launches_per_pass': len(conv_rows),
                         'avg_launch_us': 1e3 * t_ms / len(conv_rows), 'algorithmic_bytes_per_launch': byt / len(conv_rows),
                         'share_of_pass': float(sum(r['share'] for r in conv_rows)), 'peak_source': peaks['src'],
                         'tensor': {'achieved': 2e-9 * mac / t_ms, 'peak': 2 * peaks['bf16_sus'], 'unit': 'TOP/s int8 (peak = 2 x sustained bf16)',
