@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
 // EG = epilogue groups per pipeline: 2 (one group per TMEM buffer) for cout <= 32, where the epilogue is the issue-bound
 // stage and the kernels are small enough in registers for 768 threads; 1 otherwise (the group alternates buffers).
-template <int NBC, int EPI, bool FAST, int EG = ((NBC == 1 || NBC == 2) ? 2 : 1)>
+template <int NBC, int EPI, bool FAST, int EG = (NBC > 0 ? 2 : 1)>
 __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
@@ -469,7 +469,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
     TmaKernel kern = tma_pick(a.cout, a.epi, tma_fast(a));
-    return launch_k(kern, dim3(L.grid), dim3(a.cout <= 32 ? 768 : 512), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
+    return launch_k(kern, dim3(L.grid), dim3(a.cout <= TC_CT_MAXN ? 768 : 512), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq
