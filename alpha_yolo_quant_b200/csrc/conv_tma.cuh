@@ -29,9 +29,17 @@ constexpr int TMA_MAX_STAGES = 24;
 
 struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box origin offsets (tap - pad), first plane, byte offset in the slot
 struct TmaStage { int op0, nops, nchunks, chunk0; };
+constexpr int TMA_MAX_HMMA = 40;
+struct HaloMma { uint32_t a_off_lbo; uint32_t b_chunk; };              // A start (16-byte units, low 16 bits) | LBO (16-byte units) << 16; first B chunk
 struct TmaPlan {
     int nstages, nops, stride, slot_chunks;                            // slot_chunks = K chunks one ring slot can hold
-    int merged_cx, pad_[3];                                            // 1: stride-1 conv, rank-4 maps with (channel, x) merged into one 16*W byte row
+    int merged_cx;                                                     // 1: stride-1 conv, rank-4 maps with (channel, x) merged into one 16*W byte row
+    int a_slot_bytes;                                                  // bytes of one ring slot of A
+    // halo mode (3x3 stride-1 convs on 8 x 16 pixel tiles): ONE box per input segment per tile = the (8+2) x (16+2) pixel halo
+    // of np planes, [plane][18][10][16 B]; the nine taps are shifted windows of it, addressed by the MMA descriptors
+    // (start += (ky*10 + kx) * 16 B, SBO = 160 B = one halo row, LBO = distance to the chunk that forms the K = 32 pair)
+    int halo, n_hmma, halo_tx_bytes;
+    HaloMma hm[TMA_MAX_HMMA];
     TmaStage st[TMA_MAX_STAGES];
     TmaOp op[TMA_MAX_OPS];
 };
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.cout, NS = tp.NS;
-    const uint32_t a_slot_bytes = (uint32_t)pl.slot_chunks * 2048u, b_slot_bytes = (uint32_t)pl.slot_chunks * N * 16u;
+    const uint32_t a_slot_bytes = (uint32_t)pl.a_slot_bytes, b_slot_bytes = (uint32_t)pl.slot_chunks * N * 16u;
     unsigned char* sA = smem;
     unsigned char* sB = smem + (size_t)NS * a_slot_bytes;
     const size_t b_bytes = tp.resident_b ? (size_t)tp.nkc_pad * N * 16 : (size_t)NS * b_slot_bytes;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     if (elect_one()) {
                         const uint32_t bar = full0 + 8 * gs;
                         const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
-                        mbar_arrive_expect_tx(bar, (uint32_t)sg.nchunks * 2048u + (tp.resident_b ? 0u : nch_b * N * 16u));
+                        mbar_arrive_expect_tx(bar, (pl.halo ? (uint32_t)pl.halo_tx_bytes : (uint32_t)sg.nchunks * 2048u) + (tp.resident_b ? 0u : nch_b * N * 16u));
                         const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
                         for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
                             const TmaOp op = pl.op[o];
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         const int nstages = pl.nstages;
         if (tp.resident_b) mbar_wait(wfull, 0);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1 (bits 32.. of make_desc)
+        const uint32_t h_hi = (160u >> 4) | (1u << 14);            // halo mode: 8-pixel row groups are one halo row (10 pixels) apart
         const uint32_t a_lo0 = ((smem_u32(sA) & 0x3ffffu) >> 4) | ((2048u >> 4) << 16);
         const uint32_t b_lo0 = ((smem_u32(sB) & 0x3ffffu) >> 4) | ((((uint32_t)N * 16u) >> 4) << 16);
         const uint32_t a_step = a_slot_bytes >> 4, b_step = tp.resident_b ? 0u : (b_slot_bytes >> 4);
@@ -198,13 +207,23 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 if (a.dbg) d_wf += clock64() - w1;
                 tc_fence_after();
                 if (elect_one()) {
-                    uint32_t alo = a_lo0 + (uint32_t)gs * a_step;
-                    uint32_t blo = tp.resident_b ? b_lo0 + (uint32_t)sg.chunk0 * (uint32_t)N : b_lo0 + (uint32_t)gs * b_step;
-                    const int pairs = (sg.nchunks + 1) >> 1;      // an odd tail pairs with stale smem x zero weights
                     uint32_t acc = accum;
-                    for (int j = 0; j < pairs; ++j) {
-                        mma_i8_lh(dcol, alo, d_hi, blo, d_hi, idesc, acc);
-                        acc = 1; alo += 256u; blo += b_pair;
+                    if (pl.halo) {
+                        const uint32_t abase = ((smem_u32(sA) & 0x3ffffu) >> 4) + (uint32_t)gs * a_step;
+                        const int n_hmma = pl.n_hmma;
+                        for (int j = 0; j < n_hmma; ++j) {
+                            const HaloMma hmj = pl.hm[j];
+                            mma_i8_lh(dcol, abase + hmj.a_off_lbo, h_hi, b_lo0 + hmj.b_chunk * (uint32_t)N, d_hi, idesc, acc);
+                            acc = 1;
+                        }
+                    } else {
+                        uint32_t alo = a_lo0 + (uint32_t)gs * a_step;
+                        uint32_t blo = tp.resident_b ? b_lo0 + (uint32_t)sg.chunk0 * (uint32_t)N : b_lo0 + (uint32_t)gs * b_step;
+                        const int pairs = (sg.nchunks + 1) >> 1;  // an odd tail pairs with stale smem x zero weights
+                        for (int j = 0; j < pairs; ++j) {
+                            mma_i8_lh(dcol, alo, d_hi, blo, d_hi, idesc, acc);
+                            acc = 1; alo += 256u; blo += b_pair;
+                        }
                     }
                     mma_commit(empty0 + 8 * gs);                  // frees the smem slot when these MMAs retire
                     if (s == nstages - 1) mma_commit(tfull0 + 8 * (2 * m + buf));   // accumulator complete -> epilogue group m
@@ -372,9 +391,105 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     while (cols < (4 * N <= 512 ? 4 : 2) * N) cols <<= 1;        // two pipelines x two accumulator buffers (one for cout 256)
     tp.tmem_cols = cols;
 
-    // groups -> boxes (power-of-two plane counts, so that a stage never ends on an odd chunk before the tile's last stage)
     tc::TmaPlan& pl = L.pl;
-    pl.nstages = 0; pl.nops = 0; pl.stride = a.stride; pl.slot_chunks = slot_chunks;
+    pl.halo = 0; pl.n_hmma = 0; pl.halo_tx_bytes = 0;
+    L.smem = 0;
+    // ---- halo mode: 3x3 stride-1 convs whose map tiles into 8 x 16 pixel boxes ----
+    if (a.stride == 1 && a.Wout % 8 == 0 && a.Hout % 16 == 0 && a.Win == a.Wout && a.Hin == a.Hout && a.nkc >= 9 && tp.nkc_pad * N * 16 <= 96 * 1024) {
+        const int HW = 10, HH = 18, PLANE16 = HW * HH;           // halo pixels per plane (= 16-byte units)
+        struct Blk { int seg, p0, np; uint32_t reg16; };
+        Blk blk[8];
+        int nblk = 0, i = 0;
+        uint32_t reg16 = 0;                                       // running region start, 16-byte units
+        bool ok = true;
+        int addr16[160];
+        while (ok && i < a.nkc) {                                 // a block = 9 taps (raster order) x np planes of one buffer segment
+            int np = 1;
+            while (i + np < a.nkc && h_kc[i + np].pad_ == h_kc[i].pad_ && h_kc[i + np].dy == h_kc[i].dy && h_kc[i + np].dx == h_kc[i].dx &&
+                   h_kc[i + np].plane == h_kc[i].plane + np) ++np;
+            if (nblk == 8 || i + 9 * np > a.nkc || a.nkc > 160) { ok = false; break; }
+            for (int t = 0; t < 9 && ok; ++t)
+                for (int q = 0; q < np && ok; ++q) {
+                    const KChunk& k = h_kc[i + t * np + q];
+                    if (k.pad_ != h_kc[i].pad_ || k.plane != h_kc[i].plane + q || k.dy != t / 3 - 1 || k.dx != t % 3 - 1) ok = false;
+                    addr16[i + t * np + q] = (int)reg16 + q * PLANE16 + (t / 3) * HW + (t % 3);
+                }
+            blk[nblk].seg = h_kc[i].pad_; blk[nblk].p0 = h_kc[i].plane; blk[nblk].np = np; blk[nblk].reg16 = reg16;
+            ++nblk;
+            reg16 += (uint32_t)((np * PLANE16 + 7) & ~7);         // keep every box start 128-byte aligned
+            i += 9 * np;
+        }
+        const int npairs = (a.nkc + 1) / 2;
+        if (ok && npairs <= tc::TMA_MAX_HMMA && nblk <= tc::TMA_MAX_MAPS) {
+            for (int j = 0; j < npairs && ok; ++j) {
+                const int c0 = 2 * j, c1 = 2 * j + 1;
+                const int lbo = c1 < a.nkc ? addr16[c1] - addr16[c0] : 1;     // odd tail: second half = any valid smem x zero weights
+                if (lbo <= 0 || lbo >= (1 << 14) || addr16[c0] >= (1 << 14)) ok = false;
+                pl.hm[j].a_off_lbo = (uint32_t)addr16[c0] | ((uint32_t)lbo << 16);
+                pl.hm[j].b_chunk = (uint32_t)c0;
+            }
+        }
+        else ok = false;
+        if (ok) {
+            tp.bw_log = 3; tp.bh_log = 4;
+            tp.tiles_x = a.Wout >> 3; tp.tiles_y = a.Hout >> 4;
+            tp.ntiles = tp.tiles_x * tp.tiles_y * a.n;
+            tp.mul_x = tc_magic(tp.tiles_x); tp.mul_y = tc_magic(tp.tiles_y);
+            if ((unsigned long long)tp.ntiles * (unsigned)tp.tiles_x >= (1ull << 32)) ok = false;
+        }
+        if (ok) {
+            pl.halo = 1; pl.n_hmma = npairs; pl.halo_tx_bytes = 0;
+            pl.nstages = 1; pl.nops = nblk; pl.stride = 1; pl.slot_chunks = 2; pl.merged_cx = 1;
+            pl.st[0].op0 = 0; pl.st[0].nops = nblk; pl.st[0].nchunks = a.nkc; pl.st[0].chunk0 = 0;
+            for (int b = 0; b < nblk && ok; ++b) {
+                tc::TmaOp& op = pl.op[b];
+                op.map = b; op.dx = -1; op.dy = -1; op.p0 = blk[b].p0; op.dst_off = blk[b].reg16 * 16u;
+                pl.halo_tx_bytes += blk[b].np * PLANE16 * 16;
+                if (blk[b].seg < 0 || blk[b].seg >= nsegs) { ok = false; break; }
+                const TmaSeg& sg = segs[blk[b].seg];
+                const cuuint64_t gdim[4] = {(cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin, (cuuint64_t)a.n, (cuuint64_t)sg.nplanes};
+                const cuuint64_t gstr[3] = {(cuuint64_t)a.Win * 16, (cuuint64_t)a.Hin * a.Win * 16, (cuuint64_t)a.n * a.Hin * a.Win * 16};
+                const cuuint32_t box[4] = {(cuuint32_t)(HW * 16), (cuuint32_t)HH, 1, (cuuint32_t)blk[b].np};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                if (s.encode(&L.maps.m[b], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(sg.base), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) ok = false;
+            }
+            for (int q = nblk; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
+        }
+        if (ok) {
+            pl.a_slot_bytes = (int)(((size_t)reg16 * 16 + 1023) & ~(size_t)1023);
+            tp.KS = 2; tp.nst = 0; tp.lag = 0;
+            tp.resident_b = 1;
+            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
+            const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
+            const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
+            const size_t avail = 208 * 1024 - fixed - w_bytes;
+            int ns = (int)(avail / (size_t)pl.a_slot_bytes);
+            if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
+            ns &= ~3;
+            if (ns >= 4) {
+                tp.NS = ns;
+                L.smem = fixed + w_bytes + (size_t)ns * pl.a_slot_bytes;
+                L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
+                if (N <= TC_CT_MAXN) {
+                    for (int c = 0; c < N; ++c) {
+                        L.et.k1[c] = h_tab[c]; L.et.i1[c] = h_tab[N + c]; L.et.k2[c] = h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
+                        L.et.bias[c] = h_bias[c];
+                    }
+                }
+                L.ok = 1;
+                return 1;
+            }
+        }
+        pl.halo = 0; pl.n_hmma = 0;                               // not eligible after all: generic plan below
+        tp.bw_log = bw_log; tp.bh_log = bh_log;
+        tp.tiles_x = a.Wout >> bw_log; tp.tiles_y = a.Hout >> bh_log;
+        tp.ntiles = tp.tiles_x * tp.tiles_y * ((a.n + bn - 1) / bn);
+        tp.mul_x = tc_magic(tp.tiles_x); tp.mul_y = tc_magic(tp.tiles_y);
+    }
+    // groups -> boxes (power-of-two plane counts, so that a stage never ends on an odd chunk before the tile's last stage)
+    pl.nstages = 0; pl.nops = 0; pl.stride = a.stride; pl.slot_chunks = slot_chunks; pl.a_slot_bytes = slot_chunks * 2048;
     // stride 1: a tile row of bw pixels is 16*bw contiguous bytes -> describe (channel, x) as ONE dimension so the TMA moves
     // 256-byte rows instead of 16-byte ones (the x tap shift becomes a +-16 byte coordinate; dimension 0 cannot be strided,
     // so stride-2 convs keep the rank-5 form)
