@@ -200,15 +200,14 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
 
 // fixed-point epilogue for 16 consecutive channels [c0, c0+16) of one pixel.  CT: coefficients from the constant bank
 // (c0 compile-time) or from shared memory.  acc[] = raw accumulators (bias not yet added).
-// FAST: the common case -- K = 8 (clamp 127), one identity output, no accumulator tap: straight-line code.
+// FAST: the common case -- K = 8 (clamp 127), one identity output, no accumulator tap: straight-line code, FOLDED
+// coefficients (k1 / k2 hold k * 2^-s, see fixedpoint.cuh; i1 / i2 unused) and 32-bit store offsets.
 template <int EPI, bool CT, bool FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
                                              const float* __restrict__ lut_s) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
-    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
-    const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
     int r[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -217,19 +216,38 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
             acc[4 * q + j] = v;
-            if (EPI == 0) r[4 * q + j] = FAST ? silu_q127(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, half)
+            if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
                                               : silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
-            else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127(__int2float_rn(v), cf.k1[j], cf.i1[j], half)
+            else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127f(__int2float_rn(v), cf.k1[j], half)
                                                    : requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);
-            else r[4 * q + j] = FAST ? requant16_h(__int2float_rn(v), cf.k1[j], cf.i1[j], half) : requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
+            else r[4 * q + j] = FAST ? requant16_f(__int2float_rn(v), cf.k1[j], half) : requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
         }
     }
-    if (!FAST && a.acc_tap) {
+    if (FAST) {                       // every output buffer is < 4 GB (checked by the host): 32-bit offsets
+        const uint32_t npix = (uint32_t)a.n * (uint32_t)a.Hout * (uint32_t)a.Wout;
+        const uint32_t pix = ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
+        const uint32_t off = ((uint32_t)(c0 >> 4) * npix + pix) * 16u;
+        if (EPI != 2) {
+            *(uint4*)((int8_t*)a.out[0].base + off) =
+                make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
+        } else {
+            uint32_t wd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wd[j] = (uint32_t)(r[2 * j] & 0xffff) | ((uint32_t)(r[2 * j + 1] & 0xffff) << 16);
+            uint4* dst = (uint4*)((int8_t*)a.out[0].base + 2u * off);
+            dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        }
+        return;
+    }
+    const size_t npix = (size_t)a.n * a.Hout * a.Wout;
+    const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+    if (a.acc_tap) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             a.acc_tap[(((size_t)img * N + c0 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
     }
-    if (EPI == 0 && !FAST) {          // EPI_SILU, general outputs
+    if (EPI == 0) {                   // EPI_SILU, general outputs
         for (int o = 0; o < a.nout; ++o) {
             const OutSpec& os = a.out[o];
             uint32_t wd[4];
@@ -256,7 +274,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
                 *(uint4*)(pl + (p00 + W2 + 1) * 16) = v;
             }
         }
-    } else if (EPI == 0 || EPI == 1) {   // one int8 plane row
+    } else if (EPI == 1) {            // one int8 plane row
         *(uint4*)((int8_t*)a.out[0].base + ((size_t)(c0 >> 4) * npix + pix) * 16) =
             make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
     } else {                          // EPI_REQUANT16

@@ -93,7 +93,15 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     pdl_trigger();
     // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
     if (NBC == 0) {
-        for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
+        if (FAST) {                                                 // folded coefficients: rows 0 / 2 hold k * 2^-s (exact)
+            for (int i = tid; i < N; i += TMA_THREADS) {
+                tab_s[i] = __fmul_rn(a.tab[i], a.tab[N + i]);
+                tab_s[2 * N + i] = __fmul_rn(a.tab[2 * N + i], a.tab[3 * N + i]);
+                tab_s[N + i] = 0.f; tab_s[3 * N + i] = 0.f;
+            }
+        } else {
+            for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
+        }
         for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i];
     }
     if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
@@ -311,7 +319,7 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     unsigned grid = 0;
 };
 
-struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; };
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
 template <bool FAST>
@@ -350,6 +358,7 @@ static inline void tma_init(TmaState& s) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) {
@@ -368,6 +377,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.n = a.n; L.ok = 0;
     if (!s.ready) return 0;
     const int N = a.cout;
+    const bool fast = tma_fast(a);                                // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
     if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, false)) return 0;
     tc::TcParams& tp = L.tp;
     int bw_log = 4;
@@ -407,7 +417,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             int np = 1;
             while (i + np < a.nkc && h_kc[i + np].pad_ == h_kc[i].pad_ && h_kc[i + np].dy == h_kc[i].dy && h_kc[i + np].dx == h_kc[i].dx &&
                    h_kc[i + np].plane == h_kc[i].plane + np) ++np;
-            if (nblk == 8 || i + 9 * np > a.nkc || a.nkc > 160) { ok = false; break; }
+            if (nblk == 8 || i + 9 * np > a.nkc || a.nkc > 160 || np < s.halo_min_np) { ok = false; break; }
             for (int t = 0; t < 9 && ok; ++t)
                 for (int q = 0; q < np && ok; ++q) {
                     const KChunk& k = h_kc[i + t * np + q];
@@ -474,7 +484,8 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                 L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
                 if (N <= TC_CT_MAXN) {
                     for (int c = 0; c < N; ++c) {
-                        L.et.k1[c] = h_tab[c]; L.et.i1[c] = h_tab[N + c]; L.et.k2[c] = h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
+                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = h_tab[N + c];
+                        L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
                         L.et.bias[c] = h_bias[c];
                     }
                 }
@@ -574,7 +585,8 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     if (N <= TC_CT_MAXN) {
         for (int c = 0; c < N; ++c) {
-            L.et.k1[c] = h_tab[c]; L.et.i1[c] = h_tab[N + c]; L.et.k2[c] = h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
+            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = h_tab[N + c];
+            L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
             L.et.bias[c] = h_bias[c];
         }
     }

@@ -84,6 +84,20 @@ __device__ __forceinline__ int silu_q127(int acc, float k1, float i1, float k2, 
     const float pr = __fmul_rn(lut256[r1 + 128], a);
     return max(-127, floor_sat_s8(__fmaf_rd(__fmul_rn(k2, pr), i2, half)));
 }
+// Folded coefficients kp = k * 2^-s (an exact power-of-two scaling, so RN32(kp * x) == RN32(k * x) * 2^-s bit for bit):
+// floor(RN32(k*x) * 2^-s + 1/2) = floor(RD(RN32(kp*x) + 1/2)).  One coefficient per requant instead of two.
+__device__ __forceinline__ int silu_q127f(int acc, float k1p, float k2p, const float* __restrict__ lut256, float half) {
+    const float a = __int2float_rn(acc);
+    const int r1 = floor_sat_s8(__fadd_rd(__fmul_rn(k1p, a), half));
+    const float pr = __fmul_rn(lut256[r1 + 128], a);
+    return max(-127, floor_sat_s8(__fadd_rd(__fmul_rn(k2p, pr), half)));
+}
+__device__ __forceinline__ int requant8_127f(float x, float kp, float half) {
+    return max(-127, floor_sat_s8(__fadd_rd(__fmul_rn(kp, x), half)));
+}
+__device__ __forceinline__ int requant16_f(float x, float kp, float half) {
+    return max(-32767, floor_sat_s16(__fadd_rd(__fmul_rn(kp, x), half)));
+}
 __device__ __forceinline__ int requant8_127(float x, float k, float inv2s, float half) {
     return max(-127, floor_sat_s8(__fmaf_rd(__fmul_rn(k, x), inv2s, half)));
 }

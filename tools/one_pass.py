@@ -13,7 +13,7 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--passes', type=int, default=1)
-ap.add_argument('--conv', default='tcgen05')
+ap.add_argument('--conv', default='tma')
 args = ap.parse_args()
 K, sd, sc, ma = loaders.load_workload_npz(os.path.join(REPO, 'tests', 'golden', 'workload_k8.npz'))
 p = plan.compile_plan(sd, sc, ma, K)
