@@ -360,7 +360,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     return 0;
 }
 
-struct PassArgs { const float* img; int n; float* dbox_cls; float* dets; int32_t* counts; };
+struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; };
 
 // launch plan op i of a pass
 static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t st) {
@@ -376,11 +376,13 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
     switch (f[0]) {
     case OP_CONV_P1: {
         P1Args a;
-        a.img = img; a.amax = amax;
+        a.img = img; a.img_u8 = pa.img_u8; a.amax = amax;
         a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
         a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
         a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
         a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
+        a.half = 0.5f;
+        const bool fold = a.M == 127;                              // K = 8: the kernel takes folded coefficients k * 2^-s (exact)
         P1Const pc;
         const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
         const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);         // [4][16]
@@ -391,9 +393,11 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                 pc.w4[tap][co] = (unsigned)(uint8_t)w[0] | ((unsigned)(uint8_t)w[1] << 8) | ((unsigned)(uint8_t)w[2] << 16);
             }
         for (int co = 0; co < 16; ++co) {
-            pc.k1[co] = ht[co]; pc.i1[co] = ht[16 + co]; pc.k2[co] = ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
+            pc.k1[co] = fold ? ht[co] * ht[16 + co] : ht[co]; pc.i1[co] = ht[16 + co];
+            pc.k2[co] = fold ? ht[32 + co] * ht[48 + co] : ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
         }
-        CK(launch_k(conv_p1_kernel, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
+        if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
+        else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
         break;
     }
     case OP_CONV: {
@@ -449,15 +453,17 @@ static void drop_graphs(ayq_engine* e) {
 // One pass = memset + abs-max + the plan ops.  The ops between Conv_P1 and q_NMS touch only engine-owned memory, so for
 // a given pass size they are captured once into a CUDA graph (with the PDL edges) and replayed; Conv_P1 / q_NMS carry the
 // caller's pointers and are launched directly.
-static int run_pass(ayq_engine* e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
+// img (fp32) or img_u8 (uint8, ToTensor fused into the abs-max and Conv_P1 kernels): exactly one is non-null
+static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
     const int H = e->hdr.img_h, W = e->hdr.img_w;
     float* amax = (float*)(e->ws + e->off_amax);
     const bool prof = e->profiling;
-    PassArgs pa{img, n, dbox_cls, dets, counts};
+    PassArgs pa{img, img_u8, n, dbox_cls, dets, counts};
     int pe = 0;
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
-    CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
+    if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
+    else CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     if (e->debug_sync) {
         cudaError_t de = cudaStreamSynchronize(st);
@@ -528,7 +534,7 @@ extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cl
     const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
     for (int i0 = 0; i0 < n; i0 += mb) {
         const int m = (n - i0) < mb ? (n - i0) : mb;
-        rc = run_pass(e, img + (size_t)i0 * img_elems, m, dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
+        rc = run_pass(e, img + (size_t)i0 * img_elems, nullptr, m, dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
                       dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, counts + i0, st);
         if (rc) return rc;
     }
@@ -536,19 +542,6 @@ extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cl
 }
 
 // ---- host-buffer entry: double-buffered H2D / compute / D2H --------------------------------------------
-__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t total) {
-    // ToTensor(): u8 / 255 in fp32 (stage_8_torch.py:985-990)
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (size_t)gridDim.x * blockDim.x * 4) {
-        if (i + 3 < total) {
-            const uchar4 v = *(const uchar4*)(src + i);
-            *(float4*)(dst + i) = make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f),
-                                              __fdiv_rn((float)v.z, 255.f), __fdiv_rn((float)v.w, 255.f));
-        } else {
-            for (size_t j = i; j < total; ++j) dst[j] = __fdiv_rn((float)src[j], 255.f);
-        }
-    }
-}
-
 static int ensure_host_pipeline(ayq_engine* e, int m, bool u8) {
     if (!e->s_copy) {
         CK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
@@ -584,9 +577,11 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     if (!e || !img_host || !dets_host || !counts_host || n < 0) return fail(-22, "ayq_forward_host: bad arguments");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
-    const int mb = e->max_batch;
+    // pass size of the host pipeline: H2D of pass i+1 overlaps the kernels of pass i, so the first copy and the last pass are
+    // exposed -- smaller passes shorten both (64 images keep the kernels within ~10 % of their large-batch throughput)
+    const int mb = e->max_batch < 64 ? e->max_batch : 64;
     const int m_max = n < mb ? n : mb;
-    int rc = ensure_workspace(e, m_max);
+    int rc = ensure_workspace(e, n < e->max_batch ? n : e->max_batch);
     if (rc) return rc;
     rc = ensure_host_pipeline(e, m_max, u8);
     if (rc) return rc;
@@ -601,8 +596,7 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
         CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
         CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
         if (pass >= 2) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));    // d_dets[slot] still draining
-        if (u8) u8_to_f32_kernel<<<1184, 256, 0, e->s_comp>>>(e->d_img_u8[slot], e->d_img[slot], img_elems * m);
-        rc = run_pass(e, e->d_img[slot], m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
+        rc = run_pass(e, u8 ? nullptr : e->d_img[slot], u8 ? e->d_img_u8[slot] : nullptr, m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
         if (rc) return rc;
         CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
         CK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[slot], 0));

@@ -167,12 +167,14 @@ __global__ void __launch_bounds__(128) conv_dp4a_kernel(const ConvArgs a) {
 
 // ---- Conv_P1 + quant_matrix ---------------------------------------------------------------------------
 struct P1Args {
-    const float* img;           // (n,3,H,W) fp32
+    const float* img;           // (n,3,H,W) fp32 (U8 == false)
+    const uint8_t* img_u8;      // (n,3,H,W) uint8 (U8 == true): ToTensor (u8 / 255, stage_8_torch.py:985-990) happens in the kernel
     const float* amax;          // (n) per-image max|x|
     const float* lut;           // sigmoid table [2M+1]
     int n, H, W, Hout, Wout, M;
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
     int* acc_tap;
+    float half;                 // 0.5f in a register (see silu_q127f)
 };
 // weights and per-channel epilogue coefficients as a __grid_constant__ parameter: every use below has a compile-time
 // index, so they become constant-bank operands of IDP.4A / FMUL (no weight or coefficient loads in the kernel).
@@ -182,8 +184,10 @@ struct P1Const { unsigned w4[9][16]; float k1[16], i1[16], k2[16], i2[16]; int b
 // coalesced loads, quantised once (quant_matrix) and kept in smem as one packed word (c0,c1,c2,0) per pixel.
 #define P1_TW 32
 #define P1_TH 8
+template <bool U8>
 __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc) {
     __shared__ unsigned sQ[2 * P1_TH + 1][2 * P1_TW + 2];       // +1 pad word per row
+    __shared__ unsigned char qlut[256];                          // U8: quantised value of every byte, q = rint(fl32(fl32(v / 255) * s))
     __shared__ float lut_s[AYQ_LUT256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
@@ -196,6 +200,28 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
     const float amax = a.amax[img];
     const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);
     const size_t cs = (size_t)a.H * a.W;
+    if (U8) {
+        qlut[tid] = amax > 0.f ? (unsigned char)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) : 0;
+        __syncthreads();
+        const uint8_t* base = a.img_u8 + (size_t)img * 3 * cs;
+        for (int r = warp; r < 2 * P1_TH + 1; r += 8) {
+            const int iy = 2 * y0 - 1 + r;
+            const bool rowok = (unsigned)iy < (unsigned)a.H;
+            const uint8_t* rowp = base + (size_t)(rowok ? iy : 0) * a.W;
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                const int c = lane + 32 * cc;
+                if (c > 2 * P1_TW) break;
+                const int ix = 2 * x0 - 1 + c;
+                unsigned wd = 0;
+                if (rowok && (unsigned)ix < (unsigned)a.W) {
+                    const uint8_t* px = rowp + ix;
+                    wd = (unsigned)qlut[__ldg(px)] | ((unsigned)qlut[__ldg(px + cs)] << 8) | ((unsigned)qlut[__ldg(px + 2 * cs)] << 16);
+                }
+                sQ[r][c] = wd;
+            }
+        }
+    } else {
     const float* base = a.img + (size_t)img * 3 * cs;
     for (int r = warp; r < 2 * P1_TH + 1; r += 8) {
         const int iy = 2 * y0 - 1 + r;
@@ -217,6 +243,7 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
             sQ[r][c] = wd;
         }
     }
+    }
     __syncthreads();
     const int tx = tid & (P1_TW - 1), ty = tid / P1_TW;
     const int ox = x0 + tx, oy = y0 + ty;
@@ -237,8 +264,14 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
         for (int j = 0; j < 16; ++j) a.acc_tap[(((size_t)img * 16 + j) * a.Hout + oy) * a.Wout + ox] = acc[j];
     }
     int r[16];
+    if (a.M == 127) {                 // K = 8: folded coefficients (pc.k1 / pc.k2 hold k * 2^-s, see fixedpoint.cuh)
+        const float half = a.half;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = silu_q(acc[j], pc.k1[j], pc.i1[j], pc.k2[j], pc.i2[j], lut_s, a.M);
+        for (int j = 0; j < 16; ++j) r[j] = silu_q127f(acc[j], pc.k1[j], pc.k2[j], lut_s, half);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = silu_q(acc[j], pc.k1[j], pc.i1[j], pc.k2[j], pc.i2[j], lut_s, a.M);
+    }
     const size_t p = ((size_t)img * a.Hout + oy) * a.Wout + ox;
     *(uint4*)(a.out + p * 16) = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]),
                                            pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
@@ -273,6 +306,35 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
         atomicMax((int*)out + blockIdx.y, __float_as_int(m));
+    }
+}
+
+// uint8 images: max|u8 / 255| = fl32(max(u8) / 255) (the division is monotone).  grid (blocks, n); out[] zeroed first.
+__global__ void __launch_bounds__(256) absmax_u8_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, size_t per_image) {
+    pdl_trigger();
+    pdl_wait();
+    const uint8_t* base = x + (size_t)blockIdx.y * per_image;
+    unsigned m = 0;
+    const size_t nvec = per_image / 16;
+    if ((((uintptr_t)base) & 15) == 0) {
+        const uint4* b4 = (const uint4*)base;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+            const uint4 v = __ldg(b4 + i);
+            m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+        }
+        for (size_t i = nvec * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; i < per_image; i += (size_t)gridDim.x * 256) m = __vmaxu4(m, base[i]);
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < per_image; i += (size_t)gridDim.x * 256) m = __vmaxu4(m, base[i]);
+    }
+    unsigned mb = max(max(m & 0xff, (m >> 8) & 0xff), max((m >> 16) & 0xff, m >> 24));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    __shared__ unsigned sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) mb = max(mb, sm[i]);
+        atomicMax((int*)out + blockIdx.y, __float_as_int(__fdiv_rn((float)mb, 255.f)));
     }
 }
 
