@@ -44,7 +44,7 @@ struct ayq_engine {
     std::vector<OpDesc> ops;
     std::vector<unsigned char> host_data;
     unsigned char* d_data = nullptr;       // data section on the device
-    int max_batch = 64;
+    int max_batch = 256;
     int cap = 0;                           // images the workspace is sized for
     unsigned char* ws = nullptr;
     size_t ws_bytes = 0;

@@ -319,7 +319,7 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     unsigned grid = 0;
 };
 
-struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; };
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
 template <bool FAST>
@@ -358,7 +358,9 @@ static inline void tma_init(TmaState& s) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
+    if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);
+    if (const char* ev = getenv("AYQ_SMEM_KB")) s.budget_kb = atoi(ev);          // experiments: smaller CTAs let consecutive kernels co-reside
+    if (const char* ev = getenv("AYQ_RESIDENT_KB")) s.resident_kb = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) {
@@ -405,7 +407,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     pl.halo = 0; pl.n_hmma = 0; pl.halo_tx_bytes = 0;
     L.smem = 0;
     // ---- halo mode: 3x3 stride-1 convs whose map tiles into 8 x 16 pixel boxes ----
-    if (a.stride == 1 && a.Wout % 8 == 0 && a.Hout % 16 == 0 && a.Win == a.Wout && a.Hin == a.Hout && a.nkc >= 9 && tp.nkc_pad * N * 16 <= 96 * 1024) {
+    if (a.stride == 1 && a.Wout % 8 == 0 && a.Hout % 16 == 0 && a.Win == a.Wout && a.Hin == a.Hout && a.nkc >= 9 && tp.nkc_pad * N * 16 <= s.resident_kb * 1024) {
         const int HW = 10, HH = 18, PLANE16 = HW * HH;           // halo pixels per plane (= 16-byte units)
         struct Blk { int seg, p0, np; uint32_t reg16; };
         Blk blk[8];
@@ -474,7 +476,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
             const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
             const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
-            const size_t avail = 208 * 1024 - fixed - w_bytes;
+            const size_t avail = (size_t)s.budget_kb * 1024 - fixed - w_bytes;
             int ns = (int)(avail / (size_t)pl.a_slot_bytes);
             if (ns > tc::TC_MAX_NS) ns = tc::TC_MAX_NS;
             ns &= ~3;
@@ -572,8 +574,8 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
     const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
-    const size_t budget = 208 * 1024;
-    tp.resident_b = w_bytes <= 96 * 1024 ? 1 : 0;
+    const size_t budget = (size_t)s.budget_kb * 1024;
+    tp.resident_b = w_bytes <= (size_t)s.resident_kb * 1024 ? 1 : 0;
     const size_t per_slot = (size_t)slot_chunks * 2048 + (tp.resident_b ? 0 : (size_t)slot_chunks * N * 16);
     const size_t avail = budget - fixed - (tp.resident_b ? w_bytes : 0);
     int ns = (int)(avail / per_slot);

@@ -86,7 +86,7 @@ def _require_cuda(t, name):
 class Engine:
     """One handle per GPU (not thread-safe), created from a compiled plan (plan.compile_plan)."""
 
-    def __init__(self, plan, device=0, max_batch=64):
+    def __init__(self, plan, device=0, max_batch=256):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise AyqError('Engine: no CUDA device available; the integer YOLOv8n path has no CPU fallback')

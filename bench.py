@@ -174,7 +174,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
-    ap.add_argument('--max-batch', type=int, default=128, help='images per internal pass of the engine')
+    ap.add_argument('--max-batch', type=int, default=256, help='images per internal pass of the engine')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--conv', default=os.environ.get('AYQ_CONV', 'tma'), choices=['dp4a', 'tcgen05', 'tma'])
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU-baseline sample (images)')
