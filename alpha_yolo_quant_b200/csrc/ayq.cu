@@ -73,6 +73,7 @@ struct ayq_engine {
     std::vector<cudaEvent_t> prof_ev;
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
+    int fast_div = 0;                      // DFL division shortcut verified on this device (div_selfcheck_kernel)
     bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
     long long* d_role = nullptr;
     TcState tc;                            // tcgen05 path state
@@ -217,6 +218,18 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     g_pdl = getenv("AYQ_NO_PDL") == nullptr ? 1 : 0;
     tc_init(e->tc);
     tma_init(e->tma);
+    {   // exhaustive check of the DFL division shortcut: e in [0, 127], S in [1, 16 * 127]
+        int* d_bad = nullptr;
+        const int emax = 127, smax = 16 * 127;
+        if (cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess) {
+            cudaMemset(d_bad, 0, sizeof(int));
+            div_selfcheck_kernel<<<((emax + 1) * smax + 255) / 256, 256>>>(emax, smax, d_bad);
+            int bad = 1;
+            if (cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) e->fast_div = bad == 0 ? 1 : 0;
+            cudaFree(d_bad);
+        }
+        if (getenv("AYQ_NO_FAST_DIV")) e->fast_div = 0;
+    }
     e->op_ms.assign(h.n_ops + 1, 0.f);
     e->op_calls.assign(h.n_ops + 1, 0);
     *out = e;
@@ -425,6 +438,7 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         a.lut16 = (const int16_t*)(e->d_data + f[HD_LUT16_OFF]);
         a.lo16 = (const int16_t*)(e->d_data + f[HD_LO16_OFF]);
         a.mono = f[HD_MONO];
+        a.fast_div = e->fast_div;
         a.dflw = (const int*)(e->d_data + f[HD_DFLW_OFF]);
         a.anchors = (const int*)(e->d_data + f[HD_ANCH_OFF]);
         a.kd = f_from_bits(f[HD_KD]); a.id = f_from_bits(f[HD_ID]);

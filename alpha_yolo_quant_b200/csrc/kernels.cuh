@@ -204,44 +204,31 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
         qlut[tid] = amax > 0.f ? (unsigned char)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) : 0;
         __syncthreads();
         const uint8_t* base = a.img_u8 + (size_t)img * 3 * cs;
-        for (int r = warp; r < 2 * P1_TH + 1; r += 8) {
-            const int iy = 2 * y0 - 1 + r;
-            const bool rowok = (unsigned)iy < (unsigned)a.H;
-            const uint8_t* rowp = base + (size_t)(rowok ? iy : 0) * a.W;
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                const int c = lane + 32 * cc;
-                if (c > 2 * P1_TW) break;
-                const int ix = 2 * x0 - 1 + c;
-                unsigned wd = 0;
-                if (rowok && (unsigned)ix < (unsigned)a.W) {
-                    const uint8_t* px = rowp + ix;
-                    wd = (unsigned)qlut[__ldg(px)] | ((unsigned)qlut[__ldg(px + cs)] << 8) | ((unsigned)qlut[__ldg(px + 2 * cs)] << 16);
-                }
-                sQ[r][c] = wd;
-            }
-        }
-    } else {
-    const float* base = a.img + (size_t)img * 3 * cs;
-    for (int r = warp; r < 2 * P1_TH + 1; r += 8) {
-        const int iy = 2 * y0 - 1 + r;
-        const bool rowok = (unsigned)iy < (unsigned)a.H && amax > 0.f;
-        const float* rowp = base + (size_t)(rowok ? iy : 0) * a.W;
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            const int c = lane + 32 * cc;
-            if (c > 2 * P1_TW) break;
-            const int ix = 2 * x0 - 1 + c;
+        for (int i = tid; i < (2 * P1_TH + 1) * (2 * P1_TW + 1); i += 256) {      // flat over the 17 x 65 patch: balanced warps
+            const int r = i / (2 * P1_TW + 1), c = i - r * (2 * P1_TW + 1);
+            const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + c;
             unsigned wd = 0;
-            if (rowok && (unsigned)ix < (unsigned)a.W) {
-                const float* px = rowp + ix;
-                const int q0 = __float2int_rn(__fmul_rn(__ldg(px), s));
-                const int q1 = __float2int_rn(__fmul_rn(__ldg(px + cs), s));
-                const int q2 = __float2int_rn(__fmul_rn(__ldg(px + 2 * cs), s));
-                wd = pack4(q0, q1, q2, 0);
+            if ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W) {
+                const uint8_t* px = base + (unsigned)iy * (unsigned)a.W + (unsigned)ix;
+                wd = (unsigned)qlut[__ldg(px)] | ((unsigned)qlut[__ldg(px + cs)] << 8) | ((unsigned)qlut[__ldg(px + 2 * cs)] << 16);
             }
             sQ[r][c] = wd;
         }
+    } else {
+    const float* base = a.img + (size_t)img * 3 * cs;
+    const bool any = amax > 0.f;
+    for (int i = tid; i < (2 * P1_TH + 1) * (2 * P1_TW + 1); i += 256) {          // flat over the 17 x 65 patch: balanced warps
+        const int r = i / (2 * P1_TW + 1), c = i - r * (2 * P1_TW + 1);
+        const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + c;
+        unsigned wd = 0;
+        if (any && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W) {
+            const float* px = base + (unsigned)iy * (unsigned)a.W + (unsigned)ix;
+            const int q0 = __float2int_rn(__fmul_rn(__ldg(px), s));
+            const int q1 = __float2int_rn(__fmul_rn(__ldg(px + cs), s));
+            const int q2 = __float2int_rn(__fmul_rn(__ldg(px + 2 * cs), s));
+            wd = pack4(q0, q1, q2, 0);
+        }
+        sQ[r][c] = wd;
     }
     }
     __syncthreads();
@@ -381,6 +368,22 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const int8_t* __restrict
     }
 }
 
+// e / S correctly rounded from the correctly rounded reciprocal r = RN(1 / S): q0 = RN(e r), rem = e - S q0 (exact in
+// one FMA), q = RN(q0 + rem r).  For the DFL operands (integers 0 <= e <= 127, 1 <= S <= 2032) this equals the IEEE
+// division bit for bit; div_selfcheck_kernel verifies ALL operand pairs on the device when the engine is created and the
+// head falls back to __fdiv_rn if a single one differed.
+__device__ __forceinline__ float div_by_rcp(float e, float S, float r) {
+    const float q0 = __fmul_rn(e, r);
+    const float rem = __fmaf_rn(-S, q0, e);
+    return __fmaf_rn(rem, r, q0);
+}
+__global__ void div_selfcheck_kernel(int emax, int smax, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (emax + 1) * smax) return;
+    const float e = (float)(i / smax), S = (float)(i % smax + 1);
+    if (__float_as_int(div_by_rcp(e, S, __frcp_rn(S))) != __float_as_int(__fdiv_rn(e, S))) atomicAdd(bad, 1);
+}
+
 // ---- Detect head: DFL decode + class scores -----------------------------------------------------------
 struct HeadArgs {
     const int8_t* box[3];       // (4 planes, n, H, W, 16) int8, channel = side*16 + bin
@@ -389,6 +392,7 @@ struct HeadArgs {
     const int16_t* lut16;       // [65535], index l + 32767
     const int16_t* lo16;        // [65535]: smallest logit with the same table value
     int mono;                   // table is monotone: class max / argmax need two gathers instead of 80
+    int fast_div;               // div_by_rcp verified against __fdiv_rn on every DFL operand pair (ayq_create)
     const int* dflw;            // [16]
     const int* anchors;         // [A][2]
     float kd, id;
@@ -432,10 +436,19 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { e[j] = lexp[b[j] - mx + top]; S += e[j]; }        // exact: integers <= 16*M
         int d = 0;
+        if (a.fast_div) {
+            const float rS = __frcp_rn(S);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int pj = (int)__fmul_rn(__fdiv_rn(e[j], S), 127.f);                     // (y / ax_sum * 127).to(int64)  :1205
-            d += pj * dflw[j];                                                            // self.dfl(p)  :1232
+            for (int j = 0; j < 16; ++j) {
+                const int pj = (int)__fmul_rn(div_by_rcp(e[j], S, rS), 127.f);            // (y / ax_sum * 127).to(int64)  :1205
+                d += pj * dflw[j];                                                        // self.dfl(p)  :1232
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int pj = (int)__fmul_rn(__fdiv_rn(e[j], S), 127.f);
+                d += pj * dflw[j];
+            }
         }
         dq[side] = (float)requant((float)d, a.kd, a.id, 32767);                           // requantize(dfl, ..., 16)  :1236
     }
