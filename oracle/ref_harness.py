@@ -317,6 +317,69 @@ def capture_goldens(work, pkg_root, k, images_u8, keep_full, dump_dir=None):
     return out, g
 
 
+def capture_goldens_float(work, pkg_root, k, images_u8):
+    """Import the UNMODIFIED stage_8_torch.py (float Detect head + torchvision NMS) and record,
+    per image: hashes of the 63 integer conv outputs and the 57 silu() outputs (sigmoid range 7), the float
+    prediction tensor dbox_cls (84, 8400) on every 8th anchor, and the returned (boxes, classes)."""
+    g = run_stage(pkg_root, 'stage_8_torch.py')
+    model = g['model']
+    fwd_globals = g['silu'].__globals__
+    state = {}
+    real_silu = g['silu']
+    real_coord = g['coord']
+    real_conv_forward = torch.nn.Conv2d.forward
+
+    def conv_forward(self, x):
+        y = real_conv_forward(self, x)
+        state['conv_out'].append(y)
+        return y
+
+    def silu(x, scale_x, a_input):
+        r = real_silu(x, scale_x, a_input)
+        state['silu_out'].append(r[0].clone())
+        return r
+
+    def coord(pred):
+        state['dbox_cls'] = pred.clone()         # coord() rewrites the first four rows in place (:160)
+        return real_coord(pred)
+
+    fwd_globals['silu'] = silu
+    fwd_globals['coord'] = coord
+    torch.nn.Conv2d.forward = conv_forward
+    out = {}
+    try:
+        for i, img_u8 in enumerate(images_u8):
+            state.update(conv_out=[], silu_out=[], dbox_cls=None)
+            x = synth.to_input_tensor(img_u8)
+            with torch.no_grad():
+                boxes, classes = model(x)
+            assert len(state['conv_out']) == 64 and len(state['silu_out']) == 57
+            pre = f'img{i}_'
+            i32 = lambda t: t.numpy().astype(np.int32)
+            for t in state['conv_out'][:63]:
+                assert bool((t == t.round()).all())
+            out[pre + 'conv_sha'] = np.array([sha(i32(t)) for t in state['conv_out'][:63]])
+            out[pre + 'silu_sha'] = np.array([sha(i32(t)) for t in state['silu_out']])
+            d = state['dbox_cls'][0].numpy().astype(np.float32)
+            out[pre + 'dbox_cls_s8'] = d[:, ::8].copy()
+            out[pre + 'conf_max'] = d[4:].max(0)
+            out[pre + 'conf_arg'] = d[4:].argmax(0).astype(np.int16)
+            if boxes is None:
+                out[pre + 'boxes'] = np.zeros((0, 4), np.float32)
+                out[pre + 'classes'] = np.zeros((0, 2), np.float32)
+            else:
+                out[pre + 'boxes'] = boxes.numpy().astype(np.float32)
+                out[pre + 'classes'] = classes.numpy().astype(np.float32)
+            print(f'[harness] float head image {i}: ndet={len(out[pre + "boxes"])} conf range '
+                  f'{float(d[4:].max(0).min()):.3g}..{float(d[4:].max()):.3g}')
+    finally:
+        torch.nn.Conv2d.forward = real_conv_forward
+    out['n_images'] = np.array(len(images_u8))
+    import torchvision
+    out['versions'] = np.array(f'torch {torch.__version__} torchvision {torchvision.__version__} numpy {np.__version__}')
+    return out
+
+
 def export_workload(work, k, g):
     """Pack what the hot path reads from disk into one small npz."""
     main_dir = f'{k}_nano'
@@ -350,6 +413,8 @@ def main():
     ap.add_argument('--n-golden', type=int, default=12)
     ap.add_argument('--dump', default=None, help='scratch dir for full per-layer tensors (not committed)')
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
+    ap.add_argument('--float-head', type=int, default=0, metavar='N',
+                    help='only record stage_8_torch.py (float head) goldens for N images -> golden_float_k{K}.npz')
     args = ap.parse_args()
     k = args.k
     work = os.path.join(args.work, f'k{k}')
@@ -367,6 +432,12 @@ def main():
     install_stubs(calib)
     if not args.skip_pipeline:
         run_pipeline(work, pkg_root, k)
+    if args.float_head:
+        images = [synth.synth_image_u8(s) for s in range(args.float_head)]
+        gold = capture_goldens_float(work, pkg_root, k, images)
+        np.savez_compressed(os.path.join(args.out, f'golden_float_k{k}.npz'), **gold)
+        print('[harness] wrote float-head goldens to', args.out)
+        return
     images = [synth.synth_image_u8(s) for s in range(args.n_golden)]
     gold, g = capture_goldens(work, pkg_root, k, images, keep_full=(0, 1, 2), dump_dir=args.dump)
     wl = export_workload(work, k, g)
