@@ -207,6 +207,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
+    if (h.n_anchors < 1 || h.n_anchors > NMS_SORT_N) { delete e; return fail(-22, "ayq_create: %d anchors (1..%d)", h.n_anchors, NMS_SORT_N); }
+    CK(cudaFuncSetAttribute(nms_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nmsf_smem_bytes(h.n_anchors)));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
     e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
@@ -343,6 +345,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
         a.out[o].up = of[5];
     }
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
+    if (f[CF_ACC_BUF] >= 0) a.acc_tap = (int*)(e->ws + e->buf_off[f[CF_ACC_BUF]]);   // raw accumulators feed the float head
     a.half = 0.5f;
     a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * 16 : nullptr;
     if (e->conv_impl == 2) {
@@ -416,6 +419,9 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
     case OP_CONV: {
         int rc = launch_conv(e, (int)i, n, st);
         if (rc) return rc;
+        if (f[CF_ACC_BUF] >= 0 && f[CF_ACC_TAP] >= 0)             // parity taps of a float-head plan: same NCHW int32 layout
+            CK(cudaMemcpyAsync(e->acc_taps[f[CF_ACC_TAP]], e->ws + e->buf_off[f[CF_ACC_BUF]],
+                               (size_t)n * f[CF_COUT] * f[CF_HOUT] * f[CF_WOUT] * sizeof(int), cudaMemcpyDeviceToDevice, st));
         break;
     }
     case OP_POOL: {
@@ -453,6 +459,26 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         CK(launch_k(nms_kernel, dim3(n), dim3(NMS_THREADS), NMS_SMEM, st, a));
         break;
     }
+    case OP_HEAD_FLOAT: {
+        HeadFloatArgs a;
+        for (int l = 0; l < 3; ++l) {
+            a.box[l] = (const int*)(e->ws + e->buf_off[f[HF_BOX_BUF0 + l]]);
+            a.cls[l] = (const int*)(e->ws + e->buf_off[f[HF_CLS_BUF0 + l]]);
+        }
+        a.box_scale = (const float*)(e->d_data + f[HF_BOX_SCALE_OFF]);
+        a.cls_scale = (const float*)(e->d_data + f[HF_CLS_SCALE_OFF]);
+        a.dflw = (const float*)(e->d_data + f[HF_DFLW_OFF]);
+        a.n = n; a.A = A;
+        a.dbox = dbox; a.conf = (float*)conf; a.cls_id = cls; a.dbox_cls = dbox_cls;
+        CK(launch_k(head_float_kernel, dim3((unsigned)(((size_t)n * A + 127) / 128)), dim3(128), 0, st, a));
+        break;
+    }
+    case OP_NMS_FLOAT: {
+        NmsFloatArgs a;
+        a.dbox = dbox; a.conf = (const float*)conf; a.cls_id = cls; a.n = n; a.A = A; a.max_keep = NMS_MAXDET; a.dets = dets; a.counts = counts;
+        CK(launch_k(nms_float_kernel, dim3(n), dim3(NMS_THREADS), nmsf_smem_bytes(A), st, a));
+        break;
+    }
     default:
         return fail(-22, "plan op %zu has unknown kind %d", i, f[0]);
     }
@@ -487,10 +513,10 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     const size_t nops = e->ops.size();
     size_t g0 = 0, g1 = nops;                                      // graphable range [g0, g1)
     while (g0 < nops && e->ops[g0].f[0] == OP_CONV_P1) ++g0;
-    while (g1 > g0 && e->ops[g1 - 1].f[0] == OP_NMS) --g1;
+    while (g1 > g0 && (e->ops[g1 - 1].f[0] == OP_NMS || e->ops[g1 - 1].f[0] == OP_NMS_FLOAT)) --g1;
     bool graphable = e->use_graph && !prof && !e->debug_sync && !dbox_cls && e->conv_impl == 2 && g1 > g0;
     for (size_t i = g0; i < g1 && graphable; ++i)
-        if (e->ops[i].f[0] == OP_CONV_P1 || e->ops[i].f[0] == OP_NMS) graphable = false;
+        if (e->ops[i].f[0] == OP_CONV_P1 || e->ops[i].f[0] == OP_NMS || e->ops[i].f[0] == OP_NMS_FLOAT) graphable = false;
     for (size_t i = 0; i < nops; ++i) {
         if (graphable && i == g0) {
             auto it = e->graphs.find(n);
@@ -725,6 +751,30 @@ extern "C" int ayq_nms(ayq_handle e, const float* dbox_cls, int n, float* dets, 
         a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.boxes = nullptr; a.scores = nullptr; a.n = m; a.A = A; a.mode = 0; a.max_keep = NMS_MAXDET;
         a.dets = dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE; a.counts = counts + i0;
         nms_kernel<<<m, NMS_THREADS, NMS_SMEM, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ayq_coord_float(ayq_handle e, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream) {
+    if (!e || !dbox_cls || !dets || !counts || n < 0) return fail(-22, "ayq_coord_float: bad arguments");
+    if (!n) return 0;
+    CK(cudaSetDevice(e->device));
+    const int A = e->hdr.n_anchors;
+    const int mb = e->max_batch;
+    int rc = ensure_workspace(e, n < mb ? n : mb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += e->cap) {
+        const int m = (n - i0) < e->cap ? (n - i0) : e->cap;
+        float4* dbox = (float4*)(e->ws + e->off_dbox);
+        float* conf = (float*)(e->ws + e->off_conf);
+        int* cls = (int*)(e->ws + e->off_cls);
+        pred_to_cand_float_kernel<<<(unsigned)(((size_t)m * A + 127) / 128), 128, 0, st>>>(dbox_cls + (size_t)i0 * 84 * A, m, A, dbox, conf, cls);
+        NmsFloatArgs a;
+        a.dbox = dbox; a.conf = conf; a.cls_id = cls; a.n = m; a.A = A; a.max_keep = NMS_MAXDET;
+        a.dets = dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE; a.counts = counts + i0;
+        nms_float_kernel<<<m, NMS_THREADS, nmsf_smem_bytes(A), st>>>(a);
     }
     CK(cudaGetLastError());
     return 0;

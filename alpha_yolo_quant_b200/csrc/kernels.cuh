@@ -738,6 +738,269 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const NmsArgs a) {
     }
 }
 
+// ---- FLOAT Detect head of stage_8_torch.py ---------------------------------------
+// The six raw head accumulators (NCHW int32, written by the convs' accumulator outputs) are dequantised and decoded in
+// fp32: x / scale (:915-922), softmax over the 16 DFL bins + dfl conv (:930-933), dist2bbox * strides (:936), class
+// sigmoid (:939-940).  Not bit-exact by construction (the reference runs torch's CPU softmax / sigmoid); the parity
+// tests state the tolerance.  One thread per (image, anchor); every load is coalesced over consecutive anchors.
+struct HeadFloatArgs {
+    const int* box[3];          // (n, 64, H, W) int32 accumulators, channel = side*16 + bin
+    const int* cls[3];          // (n, 80, H, W) int32
+    const float* box_scale;     // [3][64]
+    const float* cls_scale;     // [3][80]
+    const float* dflw;          // [16] dfl.weight
+    int n, A;
+    float4* dbox;               // (n, A) cx cy w h
+    float* conf; int* cls_id;   // (n, A) max class probability / first arg-max
+    float* dbox_cls;            // optional (n, 84, A)
+};
+
+__global__ void __launch_bounds__(128) head_float_kernel(const HeadFloatArgs a) {
+    __shared__ float bs[3 * 64], cs[3 * 80], dw[16];
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 3 * 64; i += 128) bs[i] = a.box_scale[i];
+    for (int i = threadIdx.x; i < 3 * 80; i += 128) cs[i] = a.cls_scale[i];
+    if (threadIdx.x < 16) dw[threadIdx.x] = a.dflw[threadIdx.x];
+    __syncthreads();
+    pdl_wait();
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= a.n * a.A) return;
+    const int img = idx / a.A, an = idx % a.A;
+    int lvl, hw, local;
+    if (an < 6400) { lvl = 0; hw = 80; local = an; }
+    else if (an < 8000) { lvl = 1; hw = 40; local = an - 6400; }
+    else { lvl = 2; hw = 20; local = an - 8000; }
+    const float stride = (float)(8 << lvl);
+    const size_t hw2 = (size_t)hw * hw;
+    const int* bp = a.box[lvl] + (size_t)img * 64 * hw2 + local;
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        float x[16], mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            x[j] = __fdiv_rn((float)__ldg(bp + (size_t)(side * 16 + j) * hw2), bs[lvl * 64 + side * 16 + j]);
+            mx = fmaxf(mx, x[j]);
+        }
+        float S = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = expf(x[j] - mx); S += x[j]; }
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc = fmaf(__fdiv_rn(x[j], S), dw[j], acc);
+        d[side] = acc;
+    }
+    const float ax = (float)(local % hw) + 0.5f, ay = (float)(local / hw) + 0.5f;          // make_anchors :97-109
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];            // dist2bbox :112-121
+    const float cx = __fmul_rn(__fdiv_rn(x1 + x2, 2.f), stride), cy = __fmul_rn(__fdiv_rn(y1 + y2, 2.f), stride);
+    const float w = __fmul_rn(x2 - x1, stride), h = __fmul_rn(y2 - y1, stride);
+    a.dbox[idx] = make_float4(cx, cy, w, h);
+    float* full = a.dbox_cls ? a.dbox_cls + (size_t)img * 84 * a.A + an : nullptr;
+    if (full) { full[0] = cx; full[(size_t)a.A] = cy; full[(size_t)2 * a.A] = w; full[(size_t)3 * a.A] = h; }
+    const int* cp = a.cls[lvl] + (size_t)img * 80 * hw2 + local;
+    float best = -1.f; int bj = 0;
+#pragma unroll 8
+    for (int c = 0; c < 80; ++c) {
+        const float z = __fdiv_rn((float)__ldg(cp + (size_t)c * hw2), cs[lvl * 80 + c]);
+        const float p = __fdiv_rn(1.f, 1.f + expf(-z));                                     // sigmoid :940
+        if (full) full[(size_t)(4 + c) * a.A] = p;
+        if (p > best) { best = p; bj = c; }                                                 // first maximum, cls.max(1) :170
+    }
+    a.conf[idx] = best;
+    a.cls_id[idx] = bj;
+}
+
+// per-anchor max / first argmax from a caller-provided (n,84,A) fp32 prediction tensor (ayq_coord_float entry)
+__global__ void __launch_bounds__(128) pred_to_cand_float_kernel(const float* __restrict__ pred, int n, int A,
+                                                                 float4* dbox, float* conf, int* cls_id) {
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= n * A) return;
+    const int img = idx / A, an = idx % A;
+    const float* p = pred + (size_t)img * 84 * A + an;
+    dbox[idx] = make_float4(p[0], p[(size_t)A], p[(size_t)2 * A], p[(size_t)3 * A]);
+    float best = -INFINITY; int bj = 0;
+    for (int c = 0; c < 80; ++c) {
+        const float s = p[(size_t)(4 + c) * A];
+        if (s > best) { best = s; bj = c; }
+    }
+    conf[idx] = best;
+    cls_id[idx] = bj;
+}
+
+// coord() of stage_8_torch.py:146-190 (+ clip_boxes :240-252): candidates conf > 1e-8 (in practice all A anchors), boxes
+// offset by class * 7680, torchvision.ops.nms(boxes, scores, 0.45) = greedy over the stable descending score order,
+// j suppressed by a kept i when inter / (area_i + area_j - inter) > 0.45 with every operation rounded to fp32 in that
+// order, first 300 kept.  One CTA (1024 threads) per image; A <= 16384.
+// dynamic smem: region0 = max(8 * sort_n, 16 * A) bytes: 64-bit sort keys, then x1 y1 x2 y2 [A] | order u16[A] | diag
+// u32[32 * nchunk] | rem u32[nchunk] | kept int[300] | sh int[8]
+#define NMSF_THR 0.45f
+#define NMSF_CONF 0.00000001f
+static inline size_t nmsf_smem_bytes(int A) {
+    size_t sort_n = 64;
+    while (sort_n < (size_t)A) sort_n <<= 1;
+    const size_t r0 = 8 * sort_n > 16 * (size_t)A ? 8 * sort_n : 16 * (size_t)A;
+    const size_t nchunk = ((size_t)A + 31) / 32;
+    return r0 + (((size_t)A * 2 + 15) & ~(size_t)15) + nchunk * 32 * 4 + ((nchunk * 4 + 15) & ~(size_t)15) + NMS_MAXDET * 4 + 64;
+}
+struct NmsFloatArgs {
+    const float4* dbox; const float* conf; const int* cls_id;   // (n, A)
+    int n, A, max_keep;
+    float* dets;       // (n, 300, 6)
+    int* counts;       // (n)
+};
+
+__device__ __forceinline__ bool nmsf_suppresses(const float* __restrict__ bx, int A, int i, float jx1, float jy1, float jx2, float jy2, float jarea) {
+    const float ix1 = bx[i], iy1 = bx[A + i], ix2 = bx[2 * A + i], iy2 = bx[3 * A + i];
+    const float iarea = __fmul_rn(ix2 - ix1, iy2 - iy1);
+    const float w = fmaxf(0.f, fminf(ix2, jx2) - fmaxf(ix1, jx1)), h = fmaxf(0.f, fminf(iy2, jy2) - fmaxf(iy1, jy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+    return ovr > NMSF_THR;
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_float_kernel(const NmsFloatArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int img = blockIdx.x, tid = threadIdx.x, A = a.A;
+    const int lane = tid & 31, wid = tid >> 5;
+    int sort_cap = 64;
+    while (sort_cap < A) sort_cap <<= 1;
+    const size_t r0 = 8 * (size_t)sort_cap > 16 * (size_t)A ? 8 * (size_t)sort_cap : 16 * (size_t)A;
+    const int nchunk_max = (A + 31) >> 5;
+    unsigned long long* keys = (unsigned long long*)smem_raw;
+    float* bx = (float*)smem_raw;                                   // reuses the key region after the sort
+    unsigned short* order = (unsigned short*)(smem_raw + r0);
+    unsigned* diag = (unsigned*)(smem_raw + r0 + (((size_t)A * 2 + 15) & ~(size_t)15));
+    unsigned* rem = diag + (size_t)nchunk_max * 32;
+    int* kept = (int*)((unsigned char*)rem + (((size_t)nchunk_max * 4 + 15) & ~(size_t)15));
+    int* sh = kept + NMS_MAXDET;
+    const float* conf = a.conf + (size_t)img * A;
+    const float4* dbox = a.dbox + (size_t)img * A;
+    const int* cls_id = a.cls_id + (size_t)img * A;
+    pdl_trigger();
+    if (tid < 8) sh[tid] = 0;
+    pdl_wait();
+    __syncthreads();
+    for (int i0 = 0; i0 < A; i0 += NMS_THREADS) {                   // warp-uniform trip count
+        const int i = i0 + tid;
+        bool cand = false;
+        unsigned long long key = 0;
+        if (i < A) {
+            const float c = conf[i];
+            cand = c > NMSF_CONF;                                   // :150, :172 (positive, so the bit pattern orders like the value)
+            key = ((unsigned long long)(0xffffffffu - __float_as_uint(c)) << 32) | (unsigned)i;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+            const int leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sh[0], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cand) keys[base + __popc(bal & ((1u << lane) - 1))] = key;
+        }
+    }
+    __syncthreads();
+    const int T = sh[0];
+    if (T == 0) {                                                   // coord() leaves the empty output -> (None, None) upstream
+        if (tid == 0) a.counts[img] = 0;
+        return;
+    }
+    int sort_n = 64;
+    while (sort_n < T) sort_n <<= 1;
+    for (int i = T + tid; i < sort_n; i += NMS_THREADS) keys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= sort_n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < sort_n / 2; t += NMS_THREADS) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const unsigned long long x = keys[lo], y = keys[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < T; i += NMS_THREADS) order[i] = (unsigned short)(keys[i] & 0xffffu);
+    __syncthreads();                                                // keys are dead from here on: the region becomes bx
+    for (int i = tid; i < T; i += NMS_THREADS) {
+        const int an = order[i];
+        const float4 d = dbox[an];
+        const float dw = __fdiv_rn(d.z, 2.f), dh = __fdiv_rn(d.w, 2.f);            // xywh2xyxy :124-143
+        const float off = __fmul_rn((float)cls_id[an], 7680.f);                     // :182
+        bx[i] = (d.x - dw) + off; bx[A + i] = (d.y - dh) + off;                     // boxes = x[:, :4] + c  :186
+        bx[2 * A + i] = (d.x + dw) + off; bx[3 * A + i] = (d.y + dh) + off;
+    }
+    const int nchunk = (T + 31) >> 5;
+    for (int i = tid; i < nchunk; i += NMS_THREADS) rem[i] = 0;
+    __syncthreads();
+    // Same lazy greedy scheme as nms_kernel: diagonal 32x32 blocks first, then chunk by chunk resolve + apply kept rows.
+    for (int c = wid; c < nchunk; c += NMS_THREADS / 32) {
+        const int j = c * 32 + lane;
+        const bool jv = j < T;
+        const int jj = jv ? j : 0;
+        const float jx1 = bx[jj], jy1 = bx[A + jj], jx2 = bx[2 * A + jj], jy2 = bx[3 * A + jj];
+        const float ja = __fmul_rn(jx2 - jx1, jy2 - jy1);
+        unsigned mine = 0;
+        for (int ii = 0; ii < 32; ++ii) {
+            const int i = c * 32 + ii;
+            const bool s = jv && i < T && j > i && nmsf_suppresses(bx, A, i, jx1, jy1, jx2, jy2, ja);
+            const unsigned bits = __ballot_sync(0xffffffffu, s);
+            if (lane == ii) mine = bits;
+        }
+        diag[c * 32 + lane] = mine;
+    }
+    __syncthreads();
+    int nk = 0;                                                     // block-uniform
+    for (int c = 0; c < nchunk && nk < a.max_keep; ++c) {
+        if (wid == 0) {
+            unsigned cur = rem[c];
+            const int nrow = min(32, T - c * 32);
+            if (nrow < 32) cur |= 0xffffffffu << nrow;
+            const unsigned d = diag[c * 32 + lane];
+            unsigned keep = 0;
+            int k = nk;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const unsigned di = __shfl_sync(0xffffffffu, d, i);
+                if (!((cur >> i) & 1u) && k < a.max_keep) { keep |= 1u << i; cur |= di; ++k; }
+            }
+            if ((keep >> lane) & 1u) kept[nk + __popc(keep & ((1u << lane) - 1))] = c * 32 + lane;
+            if (lane == 0) sh[6] = (int)keep;
+        }
+        __syncthreads();
+        const unsigned keep = (unsigned)sh[6];
+        nk += __popc(keep);
+        if (keep && nk < a.max_keep) {
+            for (int wc = c + 1 + wid; wc < nchunk; wc += NMS_THREADS / 32) {
+                const int j = wc * 32 + lane;
+                const bool jv = j < T;
+                const int jj = jv ? j : 0;
+                const float jx1 = bx[jj], jy1 = bx[A + jj], jx2 = bx[2 * A + jj], jy2 = bx[3 * A + jj];
+                const float ja = __fmul_rn(jx2 - jx1, jy2 - jy1);
+                unsigned acc = 0;
+                for (unsigned m = keep; m; m &= m - 1) {
+                    const int i = c * 32 + __ffs(m) - 1;
+                    acc |= __ballot_sync(0xffffffffu, jv && nmsf_suppresses(bx, A, i, jx1, jy1, jx2, jy2, ja));
+                }
+                if (lane == 0) rem[wc] |= acc;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.counts[img] = nk;
+    for (int r = tid; r < nk; r += NMS_THREADS) {
+        const int an = order[kept[r]];
+        float* row = a.dets + ((size_t)img * NMS_MAXDET + r) * 6;
+        const float4 d = dbox[an];
+        const float dw = __fdiv_rn(d.z, 2.f), dh = __fdiv_rn(d.w, 2.f);
+        const float c4[4] = {d.x - dw, d.y - dh, d.x + dw, d.y + dh};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row[q] = fminf(fmaxf(c4[q], 0.f), 640.f);      // scale_boxes (gain 1, pad 0) + clip_boxes :203-252
+        row[4] = conf[an];
+        row[5] = (float)cls_id[an];
+    }
+}
+
 // ---- export a plane buffer as NCHW int32 (parity taps) ------------------------------------------------
 __global__ void export_planes_kernel(const void* __restrict__ src, int elem_bytes, int nplanes, int n, int H, int W, int* __restrict__ dst) {
     const size_t total = (size_t)n * nplanes * 16 * H * W;

@@ -9,7 +9,7 @@
 #include <stdint.h>
 
 #define AYQ_MAGIC 0x31515941u      // "AYQ1"
-#define AYQ_PLAN_VERSION 6
+#define AYQ_PLAN_VERSION 7
 
 struct PlanHeader {
     uint32_t magic, version;
@@ -24,7 +24,8 @@ struct BufDesc { int32_t nplanes, H, W, elem_bytes; };
 #define AYQ_OP_FIELDS 64
 struct OpDesc { int32_t f[AYQ_OP_FIELDS]; };
 
-enum { OP_CONV = 1, OP_CONV_P1 = 2, OP_POOL = 3, OP_HEAD = 4, OP_NMS = 5 };
+enum { OP_CONV = 1, OP_CONV_P1 = 2, OP_POOL = 3, OP_HEAD = 4, OP_NMS = 5,
+       OP_HEAD_FLOAT = 6, OP_NMS_FLOAT = 7 };   // stage_8_torch.py: float Detect head + coord() (torchvision NMS semantics)
 // conv epilogues
 enum { EPI_SILU = 0,        // silu() then up to AYQ_MAX_OUT stores (identity or scalar requant, optional 2x upsample)
        EPI_REQUANT8 = 1,    // per-channel requantize of the raw accumulator to K bits   (requant_last_layers)
@@ -47,7 +48,9 @@ enum {
     CF_OUT_STRIDE = 6,
     CF_LAYER = 40,                     // index into plan.LAYERS (all_scales key order)
     CF_ACC_TAP = 41,                   // -1 or index of the int32 accumulator tap (parity tests)
-    CF_NAME_OFF = 42                   // data offset of a NUL terminated layer name
+    CF_NAME_OFF = 42,                  // data offset of a NUL terminated layer name
+    CF_ACC_BUF = 43                    // -1 or an int32 buffer (elem_bytes 4) that receives the raw accumulators as NCHW (n, cout, H, W):
+                                       // the head inputs of stage_8_torch.py:915-922
 };
 
 // OP_CONV_P1: Conv_P1 reads the fp32 NCHW image, fuses the per-image input quantiser (quant_matrix)
@@ -65,3 +68,10 @@ enum { HD_BOX_BUF0 = 1,                // 3 x int8 buffers (4 planes each), P3 P
        HD_KD = 11, HD_ID = 12,         // float bits of the dfl requant coefficient and 2^-s
        HD_LO16_OFF = 13,               // int16[65535]: smallest logit with the same final-sigmoid value, index l + 32767
        HD_MONO = 14 };                 // 1 when the final sigmoid table is monotone non-decreasing
+// OP_HEAD_FLOAT: dequantise + float softmax/DFL/sigmoid decode of the six raw head accumulators (stage_8_torch.py:915-947)
+enum { HF_BOX_BUF0 = 1,                // 3 x int32 NCHW accumulator buffers (64 channels), P3 P4 P5
+       HF_CLS_BUF0 = 4,                // 3 x int32 NCHW accumulator buffers (80 channels)
+       HF_BOX_SCALE_OFF = 7,           // float[3][64] all_scales['*_up_2']
+       HF_CLS_SCALE_OFF = 8,           // float[3][80] all_scales['*_down_2']
+       HF_DFLW_OFF = 9 };              // float[16] dfl.weight
+

@@ -41,6 +41,7 @@ SIGNATURES = {
     'ayq_absmax_f32': (_int, [_vp, _vp, _int, _sz, _vp]),
     'ayq_nms': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'ayq_nms_boxes': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    'ayq_coord_float': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
 }
 
 _LIB = None
@@ -153,6 +154,17 @@ class Engine:
         dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=dbox_cls.device)
         counts = torch.empty((n,), dtype=torch.int32, device=dbox_cls.device)
         check(self.lib.ayq_nms(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
+        return dets, counts
+
+    def coord_float(self, dbox_cls):
+        """coord() of stage_8_torch.py on a (n,84,8400) float prediction tensor -> (dets (n,300,6), counts (n))."""
+        _require_cuda(dbox_cls, 'Engine.coord_float')
+        dbox_cls = dbox_cls.contiguous().float()
+        n = dbox_cls.shape[0]
+        assert tuple(dbox_cls.shape[1:]) == (84, ANCHORS)
+        dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=dbox_cls.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=dbox_cls.device)
+        check(self.lib.ayq_coord_float(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
         return dets, counts
 
     # -- taps / introspection

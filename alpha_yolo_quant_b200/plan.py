@@ -24,9 +24,9 @@ from . import lut as _lut
 
 DFL_RANGE = 14.8264799118042          # stage_8_torch_full_quant.py:436,473
 MAGIC = 0x31515941
-VERSION = 6
+VERSION = 7
 OP_FIELDS = 64
-OP_CONV, OP_CONV_P1, OP_POOL, OP_HEAD, OP_NMS = 1, 2, 3, 4, 5
+OP_CONV, OP_CONV_P1, OP_POOL, OP_HEAD, OP_NMS, OP_HEAD_FLOAT, OP_NMS_FLOAT = 1, 2, 3, 4, 5, 6, 7
 EPI_SILU, EPI_REQUANT8, EPI_REQUANT16 = 0, 1, 2
 OUT_IDENT, OUT_REQUANT = 0, 1
 MAX_OUT = 3
@@ -141,7 +141,7 @@ class LT:
 
 
 class PlanBuilder:
-    def __init__(self, sd, scales, max_a, K, sigmoid_range=6, taps=False, img=640):
+    def __init__(self, sd, scales, max_a, K, sigmoid_range=6, taps=False, img=640, head='int'):
         self.sd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in sd.items()}
         self.scales = {k: torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1) for k, v in scales.items()}
         self.max_a = max_a
@@ -150,6 +150,8 @@ class PlanBuilder:
         self.sigmoid_range = sigmoid_range
         self.taps = taps
         self.img = img
+        assert head in ('int', 'float')
+        self.head = head                # 'int': stage_8_torch_full_quant.py (DFL / scores / q_NMS in integers); 'float': stage_8_torch.py:915-961
         self.bufs = []              # (name, nplanes, H, W, elem_bytes)
         self.ops = []               # list of int lists
         self.data = bytearray()
@@ -178,7 +180,7 @@ class PlanBuilder:
         return struct.unpack('<i', struct.pack('<f', float(x)))[0]
 
     # -- layers
-    def conv(self, name, x, next_a=None, epi=EPI_SILU, outs=None, out_scale_new=None):
+    def conv(self, name, x, next_a=None, epi=EPI_SILU, outs=None, out_scale_new=None, acc_buf=False):
         """One Conv2d + epilogue.  x: LT.  outs: list of dicts {requant: (old,new)|None, up: bool} for EPI_SILU.
         Returns (list of LT (one per out), python-float scale of the silu result)."""
         w = self.sd[SD_PREFIX[name] + '.weight']
@@ -226,6 +228,7 @@ class PlanBuilder:
             self.n_acc_taps += 1
             self.info['acc_taps'].append((name, cout, hout, wout))
         f[42] = self.add_data(np.frombuffer(name.encode() + b'\0', np.uint8))
+        f[43] = self.new_buf(f'{name}.acc', cout // 16, hout, wout, 4) if acc_buf else -1     # NCHW int32 raw accumulators
         results = []
         new_scale = None
         if epi == EPI_SILU:
@@ -369,15 +372,36 @@ class PlanBuilder:
         (r7,), _ = self.c2f(LT.cat([x, sq]), 'C2F_21', ['cf2_bottle_10', 'cf2_bottle_101', 'cf2_conv_15', 'x_down_0'], 1, False)
 
         box_bufs, cls_bufs = [], []
+        fl = self.head == 'float'
         for feat, nm in ((r5, 'x_result_5'), (r6, 'x_result_6'), (r7, 'x')):               # :1039-1119
             (u,), _ = self.conv(f'{nm}_up_0', feat, f'{nm}_up_1')
             (u,), _ = self.conv(f'{nm}_up_1', u, f'{nm}_up_2')
-            (u,), _ = self.conv(f'{nm}_up_2', u, epi=EPI_REQUANT8, out_scale_new=_lut.scale(DFL_RANGE, K))   # :472-476
-            box_bufs.append(u.parts[0].addends[0][0])
+            (u,), _ = self.conv(f'{nm}_up_2', u, epi=EPI_REQUANT8, out_scale_new=_lut.scale(DFL_RANGE, K), acc_buf=fl)   # :472-476
+            box_bufs.append(self.ops[-1][43] if fl else u.parts[0].addends[0][0])
             (d,), _ = self.conv(f'{nm}_down_0', feat, f'{nm}_down_1')
             (d,), _ = self.conv(f'{nm}_down_1', d, f'{nm}_down_2')
-            (d,), _ = self.conv(f'{nm}_down_2', d, epi=EPI_REQUANT16, out_scale_new=_lut.scale(12, 16))      # :1146-1149
-            cls_bufs.append(d.parts[0].addends[0][0])
+            (d,), _ = self.conv(f'{nm}_down_2', d, epi=EPI_REQUANT16, out_scale_new=_lut.scale(12, 16), acc_buf=fl)      # :1146-1149
+            cls_bufs.append(self.ops[-1][43] if fl else d.parts[0].addends[0][0])
+        if fl:
+            # stage_8_torch.py:915-961: the head reads the six raw accumulators (the requantised copies above are unused);
+            # decode and coord() run in fp32 (head_float_kernel / nms_float_kernel)
+            dflw = self.sd['dfl.weight'].reshape(-1).astype(np.float32)
+            assert dflw.shape == (16,)
+            names = ('x_result_5', 'x_result_6', 'x')
+            f = [0] * OP_FIELDS
+            f[0] = OP_HEAD_FLOAT
+            f[1:4] = box_bufs
+            f[4:7] = cls_bufs
+            f[7] = self.add_data(np.stack([self.scales[f'{nm}_up_2'].numpy() for nm in names]).astype(np.float32))
+            f[8] = self.add_data(np.stack([self.scales[f'{nm}_down_2'].numpy() for nm in names]).astype(np.float32))
+            f[9] = self.add_data(dflw)
+            self.ops.append(f)
+            f = [0] * OP_FIELDS
+            f[0] = OP_NMS_FLOAT
+            self.ops.append(f)
+            self.info['n_anchors'] = sum((self.img // st) ** 2 for st in (8, 16, 32))
+            self.info['box_bufs'], self.info['cls_bufs'] = box_bufs, cls_bufs
+            return self
 
         # head constants :1158-1243
         _, lut_exp = _lut.cached_array('exp', DFL_RANGE, K)
@@ -455,18 +479,19 @@ class Plan:
         self.n_acc_taps = builder.n_acc_taps
         self.taps = builder.taps
         by_op = {meta['op']: nm for nm, meta in builder.info['layers'].items()}
-        generic = {OP_POOL: 'sppf_pool', OP_HEAD: 'head(dfl+scores)', OP_NMS: 'q_NMS'}
+        generic = {OP_POOL: 'sppf_pool', OP_HEAD: 'head(dfl+scores)', OP_NMS: 'q_NMS', OP_HEAD_FLOAT: 'head(float)', OP_NMS_FLOAT: 'coord(float NMS)'}
         self.op_names = [by_op.get(i, generic.get(op[0], f'op{i}')) for i, op in enumerate(builder.ops)]
 
 
-def compile_plan(state_dict, all_scales, max_a_dict, K=8, sigmoid_range=6, taps=False):
-    """state_dict: the 127-key stage_7 dict; all_scales: {layer: fp32 (1,C,1,1) or (C,)}; max_a_dict: {name: float}."""
+def compile_plan(state_dict, all_scales, max_a_dict, K=8, sigmoid_range=6, taps=False, head='int'):
+    """state_dict: the 127-key stage_7 dict; all_scales: {layer: fp32 (1,C,1,1) or (C,)}; max_a_dict: {name: float}.
+    head='int' (sigmoid_range 6) is stage_8_torch_full_quant.py; head='float' with sigmoid_range=7 is stage_8_torch.py."""
     missing = [n for n, p in LAYERS if p + '.weight' not in state_dict or n not in all_scales]
     if missing:
         raise KeyError(f'plan: missing weights/scales for {missing[:4]}...')
     if 'dfl' not in all_scales or 'dfl.weight' not in state_dict:
         raise KeyError('plan: missing dfl weight / scale')
-    return Plan(PlanBuilder(state_dict, all_scales, max_a_dict, K, sigmoid_range, taps).build())
+    return Plan(PlanBuilder(state_dict, all_scales, max_a_dict, K, sigmoid_range, taps, head=head).build())
 
 
 def header_constants(path):

@@ -138,6 +138,11 @@ def quant_matrix(matrix, k, start=False):
 def silu(x, scale_x, a_input):
     """stage_8_torch_full_quant.py:439-452: fixed-point SiLU + requantise to scale(a_input, K).
     x: conv accumulators (n,C,H,W) fp32; scale_x: fp32 (1,C,1,1) from all_scales.  Returns (tensor, new scale)."""
+    return _silu_impl(x, scale_x, a_input, SIGMOID_RANGE, K, lookup)
+
+
+def _silu_impl(x, scale_x, a_input, SIGMOID_RANGE, K, lookup):
+    """shared by stage_8_torch.silu (sigmoid range 7, stage_8_torch.py:261-276) and the full-quant silu (range 6)"""
     _need_cuda(x, 'silu')
     lib = _eng.load_library()
     xf = x.contiguous().to(torch.float32)
@@ -261,18 +266,28 @@ class Yolov8(nn.Module):
         self._engine = None                    # weights changed: recompile lazily
         return r
 
+    _HEAD = 'int'                             # stage_8_torch.Yolov8 overrides: 'float'
+
+    def _cfg(self):
+        """(configured, all_scales, max_a_dict, K, sigmoid_range) of the module this class lives in"""
+        return _state['configured'], all_scales, max_a_dict, K, SIGMOID_RANGE
+
+    def _register(self, index):
+        _nms_engine[index] = self._engine
+
     def _ensure_engine(self):
         if self._engine is not None:
             return self._engine
-        if not _state['configured']:
+        configured, scales_, max_a_, k_, sig_ = self._cfg()
+        if not configured:
             raise _eng.AyqError('call configure(main_dir=... | workload=...) before running the model (all_scales / max_a_dict)')
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise _eng.AyqError('Yolov8: move the model to a CUDA device (.to("cuda")); there is no CPU path')
         sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-        self._plan = _plan.compile_plan(sd, all_scales, max_a_dict, K, SIGMOID_RANGE, taps=self._taps)
+        self._plan = _plan.compile_plan(sd, scales_, max_a_, k_, sig_, taps=self._taps, head=self._HEAD)
         self._engine = _eng.Engine(self._plan, dev.index or 0, self._max_batch)
-        _nms_engine[dev.index or 0] = self._engine
+        self._register(dev.index or 0)
         return self._engine
 
     @property

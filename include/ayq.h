@@ -93,6 +93,11 @@ int ayq_absmax_f32(const float* x, float* out, int n, size_t per_image, void* st
 /* coord_quant() + nms_quant() + scale_boxes/clip_boxes (stage_8_torch_full_quant.py:248-423) on a
  * caller-provided prediction tensor: dbox_cls device float32 (n,84,8400). */
 int ayq_nms(ayq_handle h, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream);
+/* coord() of stage_8_torch.py:146-190 (float path) + scale_boxes / clip_boxes / convert_res
+ * (:203-258, :949-957) on a caller-provided prediction tensor dbox_cls device float32 (n,84,8400): candidates
+ * conf > 1e-8, class offsets 7680, torchvision.ops.nms semantics at IoU 0.45 (stable descending score order, fp32
+ * arithmetic in the same order), first 300.  Output layout as ayq_forward. */
+int ayq_coord_float(ayq_handle h, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream);
 /* nms_quant(dets, scores, thresh) (stage_8_torch_full_quant.py:248-294) stand-alone: boxes device float32 (nb,4)
  * xyxy, scores device float32 (nb) holding integers in [0, 131071], nb <= 16384.  keep: device float32 (1000)
  * receives the kept indices in selection order (stable tie-break), count: device int32 (1). */

@@ -286,8 +286,10 @@ class OracleYolov8:
         return self._cs(np.concatenate(parts, 1), f'{name}_conv_1', a_keys[-1])
 
     # -- whole forward
-    def forward_maps(self, img, trace=False):
-        """img float32 (N,3,640,640) in [0,1].  Returns dict with the six head maps, dbox_cls pieces."""
+    def forward_maps(self, img, trace=False, raw_head=False):
+        """img float32 (N,3,640,640) in [0,1].  Returns the three box maps and three class maps of the Detect head
+        (requantised, stage_8_torch_full_quant.py), or with raw_head=True the six raw conv accumulators with their
+        per-channel scales, which is what stage_8_torch.py:915-922 dequantises (oracle/float_head.py)."""
         K = self.K
         self.trace = {'conv': [], 'silu': [], 'requant': [], 'coeff': []} if trace else None
         x, _ = quant_input(img, K)                                                    # :708
@@ -328,11 +330,19 @@ class OracleYolov8:
             u, _ = self._cs(feat, f'{nm}_up_0', f'{nm}_up_1')
             u, _ = self._cs(u, f'{nm}_up_1', f'{nm}_up_2')
             u = self._conv(u, f'{nm}_up_2')
+            if raw_head:
+                box_maps.append((u, self.wl.scales[f'{nm}_up_2']))
+                d, _ = self._cs(feat, f'{nm}_down_0', f'{nm}_down_1')
+                d, _ = self._cs(d, f'{nm}_down_1', f'{nm}_down_2')
+                cls_acc.append((self._conv(d, f'{nm}_down_2'), self.wl.scales[f'{nm}_down_2']))
+                continue
             u = self._requant(u, self.wl.scales[f'{nm}_up_2'], scale(DFL_RANGE, K))    # requant_last_layers :472-476
             box_maps.append(u)
             d, _ = self._cs(feat, f'{nm}_down_0', f'{nm}_down_1')
             d, _ = self._cs(d, f'{nm}_down_1', f'{nm}_down_2')
             cls_acc.append((self._conv(d, f'{nm}_down_2'), self.wl.scales[f'{nm}_down_2']))
+        if raw_head:
+            return box_maps, cls_acc
         cls_maps = [self._requant(a, s, scale(12, 16), 16) for a, s in cls_acc]        # exponent_requant :1146-1149
         return box_maps, cls_maps
 

@@ -92,3 +92,43 @@ def test_requantize_edge_cases():
     assert int(k[0]) == 128 and int(s[0]) == 7          # 256 overflows 8 bits -> shift decremented
     q, _, _ = Y.requantize(np.array([[[[1000]], [[-1000]]]]), 1.0, 1.0, 8)
     assert q.reshape(-1).tolist() == [127, -127]
+
+
+# ---- stage_8_torch.py (float Detect head), oracle/float_head.py -------------------------------------------------------
+def test_float_head_oracle_matches_reference(golden_dir):
+    """golden_float_k8.npz was recorded from the UNMODIFIED stage_8_torch.py (oracle/ref_harness.py --float-head): the
+    integer activations (sigmoid range 7) bit-exact; the float prediction tensor and the detections after coord()'s
+    torchvision NMS to 1e-6 relative (identical on the recording machine: the oracle calls the same torch CPU ops)."""
+    from oracle import float_head as FH
+    g = np.load(os.path.join(golden_dir, 'golden_float_k8.npz'))
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = FH.OracleFloatHead(wl)
+    for i in (1, 3):                                     # image 1 saturates conf at 1.0 (ties: stable order matters)
+        x = synth.to_input_array([synth.synth_image_u8(i)])
+        (b, c), = o.forward(x, trace=True)
+        tr = o.int_model.trace
+        assert [sha(t.astype(np.int32)) for t in tr['conv']] == list(g[f'img{i}_conv_sha'])
+        assert [sha(t.astype(np.int32)) for t in tr['silu']] == list(g[f'img{i}_silu_sha'])
+        p = o.last['dbox_cls'][0]
+        np.testing.assert_allclose(p[:, ::8], g[f'img{i}_dbox_cls_s8'], rtol=1e-6, atol=1e-6)
+        assert np.array_equal(p[4:].argmax(0), g[f'img{i}_conf_arg'])
+        assert b.shape == g[f'img{i}_boxes'].shape
+        np.testing.assert_allclose(b, g[f'img{i}_boxes'], rtol=1e-6, atol=1e-4)
+        np.testing.assert_allclose(c, g[f'img{i}_classes'], rtol=1e-6, atol=1e-7)
+
+
+def test_float_nms_restatement_against_torchvision():
+    """nms_greedy restates torchvision.ops.nms (the dependency is not under /root/reference); when torchvision is
+    importable, check it on random boxes with heavy overlap and tied scores."""
+    tv = pytest.importorskip('torchvision')
+    import torch
+    from oracle import float_head as FH
+    rng = np.random.default_rng(3)
+    for n in (1, 50, 700):
+        xy = rng.uniform(0, 200, (n, 2)).astype(np.float32)
+        wh = rng.uniform(5, 120, (n, 2)).astype(np.float32)
+        boxes = np.concatenate((xy, xy + wh), 1).astype(np.float32)
+        scores = np.round(rng.uniform(0, 1, n), 2).astype(np.float32)          # many ties
+        keep = FH.nms_greedy(boxes, scores, 0.45)
+        ref = tv.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.45).numpy()
+        assert np.array_equal(keep, ref), n

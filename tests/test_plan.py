@@ -109,3 +109,19 @@ def test_rescale_retry_is_global():
     assert k.tolist() == [128.0, 85.0] and s.tolist() == [7.0, 7.0]
     k, s = plan.rescale_coeffs(1.0, 1.0)
     assert k.tolist() == [128.0] and s.tolist() == [7.0]
+
+
+def test_float_head_plan(golden_dir):
+    """head='float' (stage_8_torch.py): same 63 convs, six int32 NCHW accumulator buffers, OP_HEAD_FLOAT + OP_NMS_FLOAT."""
+    import os
+    from alpha_yolo_quant_b200 import loaders, plan
+    K, sd, sc, ma = loaders.load_workload_npz(os.path.join(golden_dir, 'workload_k8.npz'))
+    p = plan.compile_plan(sd, sc, ma, K, sigmoid_range=7, head='float')
+    q = plan.compile_plan(sd, sc, ma, K)
+    assert p.n_ops == q.n_ops and p.op_names[-2:] == ['head(float)', 'coord(float NMS)']
+    acc = [b for b in p.bufs if b[4] == 4]
+    assert [(b[1] * 16, b[2]) for b in acc] == [(64, 80), (80, 80), (64, 40), (80, 40), (64, 20), (80, 20)]
+    assert not [b for b in q.bufs if b[4] == 4]
+    hc = plan.header_constants(os.path.join(os.path.dirname(plan.__file__), 'csrc', 'plan_format.h'))
+    assert hc['OP_HEAD_FLOAT'] == plan.OP_HEAD_FLOAT and hc['OP_NMS_FLOAT'] == plan.OP_NMS_FLOAT and hc['CF_ACC_BUF'] == 43
+    assert hc['AYQ_PLAN_VERSION'] == plan.VERSION
