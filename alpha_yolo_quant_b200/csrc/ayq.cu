@@ -398,6 +398,7 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
         a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
         a.half = 0.5f;
+        a.ps = f[P1_OUT_PS];
         const bool fold = a.M == 127;                              // K = 8: the kernel takes folded coefficients k * 2^-s (exact)
         P1Const pc;
         const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c

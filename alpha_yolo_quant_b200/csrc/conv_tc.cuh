@@ -228,8 +228,15 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         const uint32_t pix = ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
         const uint32_t off = ((uint32_t)(c0 >> 4) * npix + pix) * 16u;
         if (EPI != 2) {
-            *(uint4*)((int8_t*)a.out[0].base + off) =
-                make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
+            const uint4 v = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
+            if (EPI == 0 && a.out[a.nout - 1].up == 2) {           // phase-split copy (alone, or next to the plain tensor)
+                const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
+                const uint32_t plane = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)N >> 4) + (uint32_t)(c0 >> 4);
+                const uint32_t poff = (((plane * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u;
+                *(uint4*)((int8_t*)a.out[a.nout - 1].base + poff) = v;
+                if (a.nout == 1) return;
+            }
+            *(uint4*)((int8_t*)a.out[0].base + off) = v;
         } else {
             uint32_t wd[8];
 #pragma unroll
@@ -264,6 +271,8 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             int8_t* base = (int8_t*)os.base;
             if (!os.up) {
                 *(uint4*)(base + ((size_t)(c0 >> 4) * npix + pix) * 16) = v;
+            } else if (os.up == 2) {   // phase-split copy for a stride-2 consumer
+                *(uint4*)(base + ps_offset(a, c0, img, oy, ox)) = v;
             } else {             // nn.Upsample(None, 2, 'nearest') then requantize (:900-903): 2x2 replicate
                 const int W2 = a.Wout * 2;
                 const size_t p00 = ((size_t)img * a.Hout * 2 + 2 * oy) * W2 + 2 * ox;

@@ -342,9 +342,13 @@ static inline TmaKernel tma_pick(int N, int epi, bool fast) { return fast ? tma_
 // FAST epilogue: clamp 127 (16-bit logits: 32767), a single identity output, no accumulator tap
 static inline bool tma_fast(const ConvArgs& a) {
     if (a.acc_tap) return false;
+    if ((unsigned long long)a.n * a.cout * a.Hout * a.Wout * (a.epi == 2 ? 2 : 1) >= (1ull << 32)) return false;   // 32-bit store offsets
     if (a.epi == 2) return true;
     if (a.M != 127) return false;
-    return a.epi == 1 || (a.nout == 1 && a.out[0].mode == 0 && !a.out[0].up);
+    if (a.epi == 1) return true;
+    // one identity output (plain or phase-split), or the plain tensor plus its phase-split copy
+    if (a.nout == 1) return a.out[0].mode == 0 && a.out[0].up != 1;
+    return a.nout == 2 && a.out[0].mode == 0 && a.out[0].up == 0 && a.out[1].mode == 0 && a.out[1].up == 2;
 }
 
 static inline void tma_init(TmaState& s) {

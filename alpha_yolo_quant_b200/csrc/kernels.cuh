@@ -42,6 +42,14 @@ struct ConvArgs {
     long long* dbg;             // AYQ_ROLE_PROF=1: per-CTA cycle counters of the warp roles [grid][16], else nullptr
 };
 
+// byte offset of the 16-byte row (channels [c0, c0+16) of output pixel (img, oy, ox)) in a phase-split buffer
+// [(y&1)*2 + (x&1)][plane][n][Hout/2][Wout/2][16]
+__device__ __forceinline__ size_t ps_offset(const ConvArgs& a, int c0, int img, int oy, int ox) {
+    const int H2 = a.Hout >> 1, W2 = a.Wout >> 1;
+    const size_t plane = (size_t)(((oy & 1) << 1) | (ox & 1)) * (a.cout >> 4) + (c0 >> 4);
+    return (((plane * a.n + img) * H2 + (oy >> 1)) * W2 + (ox >> 1)) * 16;
+}
+
 // ---- shared epilogue: 16 consecutive output channels [c0, c0+16) of one output pixel -----------------
 // acc[] already holds the bias.  pix = (img*Hout + oy)*Wout + ox.
 __device__ __forceinline__ void epilogue16(const ConvArgs& a, const int* acc, int c0, int img, int oy, int ox,
@@ -79,6 +87,8 @@ __device__ __forceinline__ void epilogue16(const ConvArgs& a, const int* acc, in
             int8_t* base = (int8_t*)os.base;
             if (!os.up) {
                 *(uint4*)(base + ((size_t)(c0 >> 4) * npix + pix) * 16) = v;
+            } else if (os.up == 2) {   // phase-split copy for a stride-2 consumer
+                *(uint4*)(base + ps_offset(a, c0, img, oy, ox)) = v;
             } else {             // nn.Upsample(None, 2, 'nearest') then requantize (:900-903): 2x2 replicate
                 const int H2 = a.Hout * 2, W2 = a.Wout * 2;
                 const size_t np2 = npix * 4;
@@ -175,6 +185,7 @@ struct P1Args {
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
     int* acc_tap;
     float half;                 // 0.5f in a register (see silu_q127f)
+    int ps;                     // 1: phase-split output [(y&1)*2+(x&1)][n][Hout/2][Wout/2][16] (input layout of the stride-2 Conv_P2)
 };
 // weights and per-channel epilogue coefficients as a __grid_constant__ parameter: every use below has a compile-time
 // index, so they become constant-bank operands of IDP.4A / FMUL (no weight or coefficient loads in the kernel).
@@ -259,7 +270,8 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = silu_q(acc[j], pc.k1[j], pc.i1[j], pc.k2[j], pc.i2[j], lut_s, a.M);
     }
-    const size_t p = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+    const size_t p = a.ps ? ((size_t)(((oy & 1) << 1) | (ox & 1)) * a.n + img) * (size_t)(a.Hout >> 1) * (a.Wout >> 1) + (size_t)(oy >> 1) * (a.Wout >> 1) + (ox >> 1)
+                          : ((size_t)img * a.Hout + oy) * a.Wout + ox;
     *(uint4*)(a.out + p * 16) = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]),
                                            pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
 }

@@ -44,7 +44,9 @@ enum {
     CF_EPI = 13, CF_CLAMP = 14,        // clamp = 2^(bits-1)-1 of the epilogue result
     CF_LUT_OFF = 15,                   // data offset: float[2*M+1] sigmoid table (EPI_SILU)
     CF_NOUT = 16,
-    CF_OUT0 = 17,                      // AYQ_MAX_OUT x {buf, plane0, mode, k (float bits), 2^-s (float bits), upsample}
+    CF_OUT0 = 17,                      // AYQ_MAX_OUT x {buf, plane0, mode, k (float bits), 2^-s (float bits), layout}; layout 0 = planes
+                                       // [plane][n][H][W][16], 1 = 2x nearest upsample, 2 = phase-split [(y&1)*2+(x&1)][plane][n][H/2][W/2][16]
+                                       // (the input layout of a stride-2 conv: every tap becomes a stride-1 box of one phase image)
     CF_OUT_STRIDE = 6,
     CF_LAYER = 40,                     // index into plan.LAYERS (all_scales key order)
     CF_ACC_TAP = 41,                   // -1 or index of the int32 accumulator tap (parity tests)
@@ -55,7 +57,8 @@ enum {
 
 // OP_CONV_P1: Conv_P1 reads the fp32 NCHW image, fuses the per-image input quantiser (quant_matrix)
 enum { P1_HOUT = 1, P1_WOUT = 2, P1_OUT_BUF = 3, P1_W_OFF = 4,   // int8[16][32]: k = (ky*3+kx)*3 + c, zero padded to 32
-       P1_BIAS_OFF = 5, P1_TAB_OFF = 6, P1_CLAMP = 7, P1_LUT_OFF = 8, P1_ACC_TAP = 9, P1_QTAP_BUF = 10 };
+       P1_BIAS_OFF = 5, P1_TAB_OFF = 6, P1_CLAMP = 7, P1_LUT_OFF = 8, P1_ACC_TAP = 9, P1_QTAP_BUF = 10,
+       P1_OUT_PS = 11 };           // 1: the output buffer is phase-split (see CF_OUT0 'upsample' = 2)
 // OP_POOL: SPPF cascade of three MaxPool2d(5,1,2); writes p1,p2,p3
 enum { PL_IN_BUF = 1, PL_IN_PLANE0 = 2, PL_NPLANES = 3, PL_OUT_BUF = 4, PL_OUT_PLANE0 = 5, PL_H = 6, PL_W = 7 };
 // OP_HEAD: DFL decode + class score max/argmax

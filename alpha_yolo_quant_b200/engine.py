@@ -177,6 +177,9 @@ class Engine:
         c, h, w = self.buffer_shape(buf)
         out = torch.empty((n, c, h, w), dtype=torch.int32, device=self.device)
         check(self.lib.ayq_export_buffer(self._h, buf, n, out.data_ptr(), _stream_ptr(self.device)))
+        if buf in self.plan.info.get('ps_bufs', ()):
+            # phase-split buffer [(y&1)*2 + (x&1)][plane][n][h][w][16] -> (n, C, 2h, 2w)
+            out = out.view(n, 2, 2, c // 4, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c // 4, 2 * h, 2 * w).contiguous()
         return out
 
     def export_acc_tap(self, tap, n):

@@ -115,8 +115,10 @@ class Part:
 class LT:
     """Logical activation tensor = channel concatenation of Parts (all at one spatial size / scale)."""
 
-    def __init__(self, parts, h, w):
+    def __init__(self, parts, h, w, ps_buf=None, ps_only=False):
         self.parts, self.h, self.w = list(parts), h, w
+        self.ps_buf = ps_buf        # buffer holding a phase-split copy [(y&1)*2 + (x&1)][plane][n][h/2][w/2][16] (for stride-2 consumers)
+        self.ps_only = ps_only      # the phase-split copy is the only materialisation (parts is empty)
 
     @property
     def nplanes(self):
@@ -141,7 +143,7 @@ class LT:
 
 
 class PlanBuilder:
-    def __init__(self, sd, scales, max_a, K, sigmoid_range=6, taps=False, img=640, head='int'):
+    def __init__(self, sd, scales, max_a, K, sigmoid_range=6, taps=False, img=640, head='int', phase_split=None):
         self.sd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in sd.items()}
         self.scales = {k: torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1) for k, v in scales.items()}
         self.max_a = max_a
@@ -151,11 +153,13 @@ class PlanBuilder:
         self.taps = taps
         self.img = img
         assert head in ('int', 'float')
+        import os as _os
+        self.phase_split = (_os.environ.get('AYQ_NO_PS') is None) if phase_split is None else bool(phase_split)
         self.head = head                # 'int': stage_8_torch_full_quant.py (DFL / scores / q_NMS in integers); 'float': stage_8_torch.py:915-961
         self.bufs = []              # (name, nplanes, H, W, elem_bytes)
         self.ops = []               # list of int lists
         self.data = bytearray()
-        self.info = {'layers': {}, 'bufs': {}, 'silu_taps': [], 'requant_taps': [], 'acc_taps': []}
+        self.info = {'layers': {}, 'bufs': {}, 'silu_taps': [], 'requant_taps': [], 'acc_taps': [], 'ps_bufs': []}
         self.coeff_log = []         # (k, s) of every requantize() in reference call order is rebuilt by tests from info
         _, lut_arr = _lut.cached_array('sigmoid', sigmoid_range, self.K)
         self.lut_off = self.add_data(lut_arr.astype(np.float32))
@@ -187,7 +191,10 @@ class PlanBuilder:
         b = self.sd[SD_PREFIX[name] + '.bias']
         cout, cin, ks, _ = w.shape
         stride = 2 if name in STRIDE2 else 1
-        assert cin == 16 * x.nplanes, (name, cin, x.nplanes)
+        use_ps = stride == 2 and x.ps_buf is not None
+        assert not x.ps_only or use_ps, name
+        nplanes_in = cin // 16
+        assert use_ps or cin == 16 * x.nplanes, (name, cin, x.nplanes)
         assert cout % 16 == 0
         hout = (x.h + 2 * (ks // 2) - ks) // stride + 1
         wout = (x.w + 2 * (ks // 2) - ks) // stride + 1
@@ -196,7 +203,18 @@ class PlanBuilder:
         # K chunks: for part, for addend, for tap, for plane
         kc, wrows = [], []
         c0 = 0
-        for part in x.parts:
+        if use_ps:
+            # stride-2 3x3 conv on the phase-split copy: tap (ky, kx) of output (oy, ox) reads input (2oy + ky - 1, 2ox + kx - 1)
+            # = phase ((ky-1)&1, (kx-1)&1) at (oy + dy, ox + dx) with dy = -1 for ky == 0 else 0: a stride-1 box per tap, so
+            # the TMA moves whole 16*bw byte rows instead of one strided 16-byte pixel at a time
+            assert ks == 3 and x.h % 2 == 0 and x.w % 2 == 0
+            for ky in range(3):
+                for kx in range(3):
+                    ph = (((ky - 1) & 1) << 1) | ((kx - 1) & 1)
+                    for pl in range(nplanes_in):
+                        kc.append((x.ps_buf, ph * nplanes_in + pl, 0 if ky == 0 else 1, 0 if kx == 0 else 1))
+                        wrows.append(wq[:, 16 * pl:16 * pl + 16, ky, kx])
+        for part in ([] if use_ps else x.parts):
             for (buf, p0) in part.addends:
                 for ky in range(ks):
                     for kx in range(ks):
@@ -214,6 +232,8 @@ class PlanBuilder:
         f = [0] * OP_FIELDS
         f[0] = OP_CONV
         f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8] = ks, stride, x.h, x.w, hout, wout, cout, nkc
+        if use_ps:
+            f[2], f[3], f[4] = 1, x.h // 2, x.w // 2
         f[9] = self.add_data(np.array(kc, np.int32))
         f[10] = self.add_data(wpack)
         bq = np.rint(b).astype(np.int64)
@@ -240,13 +260,26 @@ class PlanBuilder:
             f[14] = self.MK
             outs = outs if outs is not None else [dict(requant=None, up=False)]
             outs = list(outs)
+            if not self.phase_split:
+                outs = [o for o in outs if not o.get('ps')] or [dict(requant=None, up=False)]
             n_req = len(outs)
-            if self.taps and all(o['requant'] is not None or o['up'] for o in outs):
+            if self.taps and all(o['requant'] is not None or o['up'] or o.get('ps') for o in outs):
                 outs.append(dict(requant=None, up=False, tap=True))                       # raw silu result for parity tests
             assert len(outs) <= MAX_OUT
             f[16] = len(outs)
+            ps_of = None
             for i, o in enumerate(outs):
                 up = 2 if o['up'] else 1
+                if o.get('ps'):
+                    assert o['requant'] is None and not o['up'] and hout % 2 == 0 and wout % 2 == 0
+                    ob = self.new_buf(f'{name}.out{i}.ps', 4 * (cout // 16), hout // 2, wout // 2)
+                    self.info['ps_bufs'].append(ob)
+                    base = 17 + 6 * i
+                    f[base], f[base + 1], f[base + 2], f[base + 3], f[base + 4], f[base + 5] = ob, 0, OUT_IDENT, self.fbits(1.0), self.fbits(1.0), 2
+                    ps_of = ob
+                    results.append(LT([], hout, wout, ps_buf=ob, ps_only=True))
+                    self.info['layers'].setdefault(name, {})['ps_buf'] = ob
+                    continue
                 ob = self.new_buf(f'{name}.out{i}', cout // 16, hout * up, wout * up)
                 base = 17 + 6 * i
                 f[base], f[base + 1] = ob, 0
@@ -274,12 +307,20 @@ class PlanBuilder:
             self.info['layers'].setdefault(name, {})['requant_bufs'] = [(ob, False)]
         if epi == EPI_SILU:
             results = results[:n_req]
+            if len(results) > 1 and any(r.ps_only for r in results):
+                # a phase-split copy next to the plain tensor: attach it to the first plain result, callers see one tensor less
+                plain = [r for r in results if not r.ps_only]
+                plain[0].ps_buf = [r for r in results if r.ps_only][0].ps_buf
+                results = plain
         self.ops.append(f)
         self.info['layers'][name].update(dict(op=len(self.ops) - 1, cout=cout, hout=hout, wout=wout, nkc=nkc,
                                                ks=ks, stride=stride, macs=cout * cin * ks * ks * hout * wout,
-                                               in_bytes=len(set((b_, p_) for b_, p_, _, _ in kc)) * x.h * x.w * 16,
+                                               in_bytes=len(set((b_, p_) for b_, p_, _, _ in kc)) * x.h * x.w * 16 // (4 if use_ps else 1),
+                                               # algorithmic output bytes: a phase-split COPY of a tensor that is also stored plain
+                                               # is a layout choice, not algorithmic traffic
                                                out_bytes=sum(self.bufs[f[17 + 6 * i]][1] * self.bufs[f[17 + 6 * i]][2] * self.bufs[f[17 + 6 * i]][3]
-                                                             * 16 * self.bufs[f[17 + 6 * i]][4] for i in range(f[16])),
+                                                             * 16 * self.bufs[f[17 + 6 * i]][4] for i in range(f[16])
+                                                             if not (f[17 + 6 * i + 5] == 2 and f[16] > 1)),
                                                kmacs=cout * 16 * nkc * hout * wout))
         return results, new_scale
 
@@ -299,7 +340,10 @@ class PlanBuilder:
         new_scale = _lut.scale(self.max_a[next_a], self.K)
         k2, i2 = _k_inv(_lut.scale(1, self.K) * sx, new_scale)
         h = self.img // 2
-        ob = self.new_buf('Conv_P1.out0', 1, h, h)
+        ps = self.phase_split and h % 2 == 0
+        ob = self.new_buf('Conv_P1.out0', 4, h // 2, h // 2) if ps else self.new_buf('Conv_P1.out0', 1, h, h)
+        if ps:
+            self.info['ps_bufs'].append(ob)
         f = [0] * OP_FIELDS
         f[0] = OP_CONV_P1
         f[1], f[2], f[3] = h, h, ob
@@ -310,6 +354,7 @@ class PlanBuilder:
         f[8] = self.lut_off
         f[9] = -1
         f[10] = -1
+        f[11] = 1 if ps else 0                                       # P1_OUT_PS: phase-split output (its only consumer is the stride-2 Conv_P2)
         if self.taps:
             f[9] = self.n_acc_taps
             self.n_acc_taps += 1
@@ -318,6 +363,8 @@ class PlanBuilder:
         self.info['layers'][name] = dict(op=len(self.ops) - 1, silu_buf=ob, cout=16, hout=h, wout=h, nkc=2, ks=3, stride=2,
                                          macs=16 * 27 * h * h, kmacs=16 * 32 * h * h,
                                          in_bytes=4 * 3 * self.img * self.img, out_bytes=16 * h * h)
+        if ps:
+            return LT([], h, h, ps_buf=ob, ps_only=True), new_scale
         return LT([Part(1, [(ob, 0)])], h, h), new_scale
 
     def c2f(self, x, name, a_keys, n_bottle, add, final_outs=None):
@@ -340,11 +387,12 @@ class PlanBuilder:
         S = lambda key: _lut.scale(self.max_a[key], K)
         x, _ = self.conv_p1('conv_p2')
         (x,), _ = self.conv('Conv_P2', x, 'conv_0_c2f')
-        (x,), _ = self.c2f(x, 'C2F_2', ['conv_b_0_c2f', 'conv_b_1_c2f', 'conv_b_2_c2f', 'conv_p3'], 1, True)
+        PS, ID = dict(requant=None, up=False, ps=True), dict(requant=None, up=False)
+        (x,), _ = self.c2f(x, 'C2F_2', ['conv_b_0_c2f', 'conv_b_1_c2f', 'conv_b_2_c2f', 'conv_p3'], 1, True, final_outs=[PS])
         (x,), _ = self.conv('Conv_P3', x, 'conv_2_c2f')
-        (r1,), s1 = self.c2f(x, 'C2F_4', ['conv_b1_c2f', 'conv_b2_c2f', 'conv_b3_c2f', 'conv_b4_c2f', 'conv_b5_c2f', 'conv_5'], 2, True)
+        (r1,), s1 = self.c2f(x, 'C2F_4', ['conv_b1_c2f', 'conv_b2_c2f', 'conv_b3_c2f', 'conv_b4_c2f', 'conv_b5_c2f', 'conv_5'], 2, True, final_outs=[ID, PS])
         (x,), _ = self.conv('Conv_P4', r1, 'cf2_conv_4')
-        (r2,), s2 = self.c2f(x, 'C2F_6', ['cf2_bconv_4', 'cf2_bconv1_4', 'cf2_bconv_5', 'cf2_bconv1_5', 'cf2_6_conv_last', 'conv7'], 2, True)
+        (r2,), s2 = self.c2f(x, 'C2F_6', ['cf2_bconv_4', 'cf2_bconv1_4', 'cf2_bconv_5', 'cf2_bconv1_5', 'cf2_6_conv_last', 'conv7'], 2, True, final_outs=[ID, PS])
         (x,), _ = self.conv('Conv_P5', r2, 'cf2_conv_6')
         (x,), _ = self.c2f(x, 'C2F_8', ['cf2_bottle_6', 'cf2_bottle_61', 'cf2_conv_7', 'sppf_conv_1'], 1, True)
         # SPPF :875-897
@@ -365,9 +413,9 @@ class PlanBuilder:
         s3_16 = S('cf2_conv_12')                    # scale of the Conv_16 output (:969-975)
         (u4, r4q), _ = self.c2f(LT.cat([u, r2]), 'C2F_12', ['cf2_conv_80', 'cf2_conv_81', 'cf2_conv_9', 'cf2_conv_10'], 1, False,
                                 final_outs=[dict(requant=(s4, s1), up=True), dict(requant=(s4, s3_16), up=False)])
-        (r5,), _ = self.c2f(LT.cat([u4, r1]), 'C2F_15', ['cf2_bottle_8', 'cf2_bottle_81', 'cf2_conv_11', 'conv8'], 1, False)
+        (r5,), _ = self.c2f(LT.cat([u4, r1]), 'C2F_15', ['cf2_bottle_8', 'cf2_bottle_81', 'cf2_conv_11', 'conv8'], 1, False, final_outs=[ID, PS])
         (x,), _ = self.conv('Conv_16', r5, 'cf2_conv_12')
-        (r6,), _ = self.c2f(LT.cat([x, r4q]), 'C2F_18', ['cf2_bottle_9', 'cf2_bottle_90', 'cf2_conv_13', 'conv9'], 1, False)
+        (r6,), _ = self.c2f(LT.cat([x, r4q]), 'C2F_18', ['cf2_bottle_9', 'cf2_bottle_90', 'cf2_conv_13', 'conv9'], 1, False, final_outs=[ID, PS])
         (x,), _ = self.conv('Conv_19', r6, 'cf2_conv_14')
         (r7,), _ = self.c2f(LT.cat([x, sq]), 'C2F_21', ['cf2_bottle_10', 'cf2_bottle_101', 'cf2_conv_15', 'x_down_0'], 1, False)
 

@@ -328,8 +328,13 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         ref = CpuReference()
-        n_cpu = max(args.cpu_images, 2 * ref.workers)
-        r, dt, _ = ref.rate(n_cpu)
+        # bounded sample of the same workload: chunks of two images per core until >= ~12 s of CPU work (at most 60 s)
+        chunk = max(args.cpu_images, 2 * ref.workers)
+        n_cpu, dt = 0, 0.0
+        while dt < 12.0 and n_cpu < 4096:
+            _, d, _ = ref.rate(chunk, seed0=100 + n_cpu)
+            n_cpu += chunk; dt += d
+        r = n_cpu / dt
         ref.close()
         cpu = {'value': r, 'unit': 'images/s', 'cores': ref.workers, 'kind': 'port',
                'sample': f'{n_cpu} synthetic images in {dt:.1f} s, numpy oracle of stage_8_torch_full_quant (oracle/yolo_int.py), '
