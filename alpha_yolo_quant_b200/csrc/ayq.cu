@@ -352,7 +352,8 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
         TmaLaunch& L = e->tma_cache[opi];
         const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
         const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
-        if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias);
+        if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
+                                  (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
         if (L.ok) {
             if (tma_launch(L, a, st) == 0) return 0;
             return fail(-5, "TMA conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
@@ -413,7 +414,17 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
             pc.k1[co] = fold ? ht[co] * ht[16 + co] : ht[co]; pc.i1[co] = ht[16 + co];
             pc.k2[co] = fold ? ht[32 + co] * ht[48 + co] : ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
         }
-        if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
+        long long sw[16];
+        for (int co = 0; co < 16; ++co) { sw[co] = 0; for (int k = 0; k < 27; ++k) sw[co] += hw[co * 32 + k] < 0 ? -hw[co * 32 + k] : hw[co * 32 + k]; }
+        const bool lean = fold && !a.acc_tap && H == 2 * a.Hout && W == 2 * a.Wout && a.Wout % P1_TW == 0 && a.Hout % P1_TH == 0 && W % 4 == 0 &&
+                          (unsigned long long)n * a.Hout * a.Wout < (1ull << 28) &&
+                          (pa.img_u8 ? ((uintptr_t)pa.img_u8 & 3) == 0 : ((uintptr_t)img & 15) == 0) &&
+                          magic_coeffs_ok(16, a.M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
+        if (lean) {                                                // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
+            for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }
+            if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(a.Wout / P1_TW, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
+            else CK(launch_k(conv_p1_fast_kernel<false>, dim3(a.Wout / P1_TW, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
+        } else if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
         else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
         break;
     }

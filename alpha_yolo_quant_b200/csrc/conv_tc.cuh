@@ -202,7 +202,7 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
 // (c0 compile-time) or from shared memory.  acc[] = raw accumulators (bias not yet added).
 // FAST: the common case -- K = 8 (clamp 127), one identity output, no accumulator tap: straight-line code, FOLDED
 // coefficients (k1 / k2 hold k * 2^-s, see fixedpoint.cuh; i1 / i2 unused) and 32-bit store offsets.
-template <int EPI, bool CT, bool FAST>
+template <int EPI, bool CT, int FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
                                              const float* __restrict__ lut_s) {
@@ -216,7 +216,8 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
             acc[4 * q + j] = v;
-            if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
+            if (EPI == 0 && FAST == 2) r[4 * q + j] = silu_magic(v, cf.k1[j], cf.i1[j], cf.k2[j], (const float2*)lut_s, half);   // b = bias + magic, i1 = -k1p * C
+            else if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
                                               : silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
             else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127f(__int2float_rn(v), cf.k1[j], half)
                                                    : requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);
@@ -228,7 +229,8 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         const uint32_t pix = ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
         const uint32_t off = ((uint32_t)(c0 >> 4) * npix + pix) * 16u;
         if (EPI != 2) {
-            const uint4 v = make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
+            const uint4 v = FAST == 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
+                                      : make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
             if (EPI == 0 && a.out[a.nout - 1].up == 2) {           // phase-split copy (alone, or next to the plain tensor)
                 const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
                 const uint32_t plane = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)N >> 4) + (uint32_t)(c0 >> 4);

@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
 // EG = epilogue groups per pipeline: 2 (one group per TMEM buffer) for cout <= 32, where the epilogue is the issue-bound
 // stage and the kernels are small enough in registers for 768 threads; 1 otherwise (the group alternates buffers).
-template <int NBC, int EPI, bool FAST, int EG = (NBC > 0 ? 2 : 1)>
+template <int NBC, int EPI, int FAST, int EG = (NBC > 0 ? 2 : 1)>
 __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
@@ -95,16 +95,18 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     if (NBC == 0) {
         if (FAST) {                                                 // folded coefficients: rows 0 / 2 hold k * 2^-s (exact)
             for (int i = tid; i < N; i += TMA_THREADS) {
-                tab_s[i] = __fmul_rn(a.tab[i], a.tab[N + i]);
+                const float k1p = __fmul_rn(a.tab[i], a.tab[N + i]);
+                tab_s[i] = k1p;
                 tab_s[2 * N + i] = __fmul_rn(a.tab[2 * N + i], a.tab[3 * N + i]);
-                tab_s[N + i] = 0.f; tab_s[3 * N + i] = 0.f;
+                tab_s[N + i] = FAST == 2 ? -__fmul_rn(k1p, AYQ_MAGIC_F) : 0.f; tab_s[3 * N + i] = 0.f;
             }
         } else {
             for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
         }
-        for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i];
+        for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i] + (FAST == 2 ? AYQ_MAGIC_I : 0);
     }
-    if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
+    if (EPI == 0 && FAST == 2) fill_lut256_magic((float2*)lut_s, a.lut, a.M, tid, TMA_THREADS);
+    else if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
@@ -317,12 +319,13 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     tc::TmaMaps maps;
     size_t smem = 0;
     unsigned grid = 0;
+    int fast = 0;             // epilogue variant: 0 generic, 1 FAST (folded coefficients), 2 MAGIC (silu_magic)
 };
 
 struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
-template <bool FAST>
+template <int FAST>
 static inline TmaKernel tma_pick_t(int N, int epi) {
     using namespace tc;
     if (epi == 0) {
@@ -334,11 +337,12 @@ static inline TmaKernel tma_pick_t(int N, int epi) {
         default: return (N % 32 == 0) ? conv_tma_kernel<0, 0, FAST> : nullptr;
         }
     }
-    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, FAST> : (N % 32 == 0 ? conv_tma_kernel<0, 1, FAST> : nullptr);
-    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, FAST> : (N % 32 == 0 ? conv_tma_kernel<0, 2, FAST> : nullptr);
+    constexpr int F = FAST ? 1 : 0;                               // the magic variant only exists for the SiLU epilogue
+    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, F> : (N % 32 == 0 ? conv_tma_kernel<0, 1, F> : nullptr);
+    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, F> : (N % 32 == 0 ? conv_tma_kernel<0, 2, F> : nullptr);
     return nullptr;
 }
-static inline TmaKernel tma_pick(int N, int epi, bool fast) { return fast ? tma_pick_t<true>(N, epi) : tma_pick_t<false>(N, epi); }
+static inline TmaKernel tma_pick(int N, int epi, int fast) { return fast == 2 ? tma_pick_t<2>(N, epi) : fast ? tma_pick_t<1>(N, epi) : tma_pick_t<0>(N, epi); }
 // FAST epilogue: clamp 127 (16-bit logits: 32767), a single identity output, no accumulator tap
 static inline bool tma_fast(const ConvArgs& a) {
     if (a.acc_tap) return false;
@@ -351,12 +355,48 @@ static inline bool tma_fast(const ConvArgs& a) {
     return a.nout == 2 && a.out[0].mode == 0 && a.out[0].up == 0 && a.out[1].mode == 0 && a.out[1].up == 2;
 }
 
+// MAGIC epilogue (fixedpoint.cuh: silu_magic) is exact iff, for every output channel, (1) |bias| + 127 * sum|w| < 2^22, so
+// that accumulator + bias + 0x4B400000 reinterprets as 1.5 * 2^23 + acc, and (2) the SiLU result can never reach -128, so
+// that the saturating conversion alone implements the clamp to [-127, 127]: for a negative accumulator with first requant
+// r1 (> -128) we have acc >= (r1 - 1/2) / k1p, hence k2p * lut[r1] * acc >= k2p * lut[r1] * (r1 - 1/2) / k1p; r1 = -128 is the
+// saturated end where the table must be 0.  Both are checked here on the host from the plan's weights and coefficients.
+static inline bool magic_coeffs_ok(int N, int M, const float* h_tab, const int* h_bias, const float* h_lut, const long long* sum_abs_w) {
+    if (M != 127 || !h_lut || getenv("AYQ_NO_MAGIC")) return false;
+    if (h_lut[0] != 0.f) return false;                            // table[-M]: value used by every saturated negative r1
+    for (int c = 0; c < N; ++c) {
+        const long long bound = (h_bias[c] < 0 ? -(long long)h_bias[c] : h_bias[c]) + 127ll * sum_abs_w[c];
+        if (bound >= (1ll << 22) - 1) return false;
+        const double k1p = (double)h_tab[c] * h_tab[N + c], k2p = (double)h_tab[2 * N + c] * h_tab[3 * N + c];
+        if (!(k1p > 0.0) || !(k2p > 0.0)) return false;
+        for (int r1 = -M; r1 < 0; ++r1) {
+            const double l = h_lut[r1 + M];
+            if (l < 0.0) return false;
+            if (k2p * l * (r1 - 0.5) / k1p * 1.001 < -126.5) return false;
+        }
+    }
+    return true;
+}
+static inline bool magic_epilogue_ok(const ConvArgs& a, const float* h_tab, const int* h_bias, const float* h_lut, const int8_t* h_w, int nkc_pad) {
+    if (a.epi != 0 || !h_w || a.cout > 256) return false;
+    const int N = a.cout;
+    long long sw[256];
+    for (int c = 0; c < N; ++c) {
+        long long t = 0;
+        for (int k = 0; k < nkc_pad; ++k) {
+            const int8_t* w = h_w + ((size_t)k * N + c) * 16;
+            for (int j = 0; j < 16; ++j) t += w[j] < 0 ? -w[j] : w[j];
+        }
+        sw[c] = t;
+    }
+    return magic_coeffs_ok(N, a.M, h_tab, h_bias, h_lut, sw);
+}
+
 static inline void tma_init(TmaState& s) {
     const int ns[] = {16, 32, 64, 80, 128};
     for (int epi = 0; epi < 3; ++epi)
         for (int N : ns)
-            for (int fast = 0; fast < 2; ++fast) {
-                TmaKernel k = tma_pick(N, epi, fast != 0);
+            for (int fast = 0; fast < 3; ++fast) {
+                TmaKernel k = tma_pick(N, epi, fast);
                 if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
             }
     int dev = 0;
@@ -379,12 +419,14 @@ struct TmaSeg { const void* base; int nplanes; };   // base = first byte of the 
 
 // Build the launch record.  h_kc: K-chunk list (pad_ = index into segs).  Returns L.ok.
 static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, const KChunk* h_kc, const TmaSeg* segs, int nsegs,
-                              const float* h_tab, const int* h_bias) {
+                              const float* h_tab, const int* h_bias, const float* h_lut = nullptr, const int8_t* h_w = nullptr) {
     L.n = a.n; L.ok = 0;
     if (!s.ready) return 0;
     const int N = a.cout;
     const bool fast = tma_fast(a);                                // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
-    if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, false)) return 0;
+    const bool magic = fast && magic_epilogue_ok(a, h_tab, h_bias, h_lut, h_w, (a.nkc + 1) & ~1);
+    L.fast = magic ? 2 : fast ? 1 : 0;
+    if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, 0)) return 0;
     tc::TcParams& tp = L.tp;
     int bw_log = 4;
     while (bw_log > 0 && (a.Wout % (1 << bw_log))) --bw_log;
@@ -477,7 +519,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             pl.a_slot_bytes = (int)(((size_t)reg16 * 16 + 1023) & ~(size_t)1023);
             tp.KS = 2; tp.nst = 0; tp.lag = 0;
             tp.resident_b = 1;
-            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
+            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 : 0;        // float2 entries for the MAGIC epilogue
             const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
             const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
             const size_t avail = (size_t)s.budget_kb * 1024 - fixed - w_bytes;
@@ -490,9 +532,9 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                 L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
                 if (N <= TC_CT_MAXN) {
                     for (int c = 0; c < N; ++c) {
-                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = h_tab[N + c];
+                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = magic ? -(L.et.k1[c] * AYQ_MAGIC_F) : h_tab[N + c];
                         L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
-                        L.et.bias[c] = h_bias[c];
+                        L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
                     }
                 }
                 L.ok = 1;
@@ -575,7 +617,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     }
     for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
     // shared memory budget
-    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;
+    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 : 0;        // float2 entries for the MAGIC epilogue
     const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = (size_t)s.budget_kb * 1024;
@@ -591,9 +633,9 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     if (N <= TC_CT_MAXN) {
         for (int c = 0; c < N; ++c) {
-            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = h_tab[N + c];
+            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = magic ? -(L.et.k1[c] * AYQ_MAGIC_F) : h_tab[N + c];
             L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
-            L.et.bias[c] = h_bias[c];
+            L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
         }
     }
     L.ok = 1;
@@ -601,7 +643,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 }
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
-    TmaKernel kern = tma_pick(a.cout, a.epi, tma_fast(a));
+    TmaKernel kern = tma_pick(a.cout, a.epi, L.fast);
     return launch_k(kern, dim3(L.grid), dim3(a.cout <= TC_CT_MAXN ? 768 : 512), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 

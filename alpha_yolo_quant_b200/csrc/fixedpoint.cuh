@@ -92,6 +92,38 @@ __device__ __forceinline__ int silu_q127f(int acc, float k1p, float k2p, const f
     const float pr = __fmul_rn(lut256[r1 + 128], a);
     return max(-127, floor_sat_s8(__fadd_rd(__fmul_rn(k2p, pr), half)));
 }
+// MAGIC variant (no int->float conversion, no lower clamp).  The accumulator arrives as m = 1.5 * 2^23 + acc, built by an
+// INTEGER add of (bias + 0x4B400000) to the raw accumulator and reinterpreted as a float: exact for |acc| < 2^22 (the host
+// proves the bound per layer from the weights).  Then
+//   RN(kp * acc)      = fma_rn(kp, m, -kp * C)     C = 1.5 * 2^23; kp * C = k * 3 * 2^(22-s) is exact, so the FMA's single
+//   RN(lut[r1] * acc) = fma_rn(l, m, -l * C)       rounding sees exactly kp * (m - C) = kp * acc (the table holds (l, -l*C))
+// and the final saturating conversion needs no max(-127, .) when the host has shown that no accumulator can reach -128
+// (SiLU is bounded below; see magic_epilogue_ok in conv_tma.cuh).
+#define AYQ_MAGIC_F 12582912.0f
+#define AYQ_MAGIC_I 0x4B400000
+__device__ __forceinline__ int silu_magic(int acc_plus_bias_magic, float k1p, float c1, float k2p, const float2* __restrict__ lut2, float half) {
+    const float m = __int_as_float(acc_plus_bias_magic);
+    const int r1 = floor_sat_s8(__fadd_rd(__fmaf_rn(k1p, m, c1), half));
+    const float2 l = lut2[r1 + 128];
+    const float pr = __fmaf_rn(l.x, m, l.y);
+    return floor_sat_s8(__fadd_rd(__fmul_rn(k2p, pr), half));
+}
+__device__ __forceinline__ void fill_lut256_magic(float2* __restrict__ dst, const float* __restrict__ table /*[2M+1]*/, int M,
+                                                  int tid, int nthreads) {
+    for (int i = tid; i < AYQ_LUT256; i += nthreads) {
+        const int r = max(-M, min(M, i - 128));
+        const float l = table[r + M];
+        dst[i] = make_float2(l, -__fmul_rn(l, AYQ_MAGIC_F));
+    }
+}
+// four values already in [-128, 127] -> one word (cvt.pack: two instructions instead of three logic ops)
+__device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d) {
+    // cvt.pack d, x, y, z:  d = (z << 16) | (sat8(x) << 8) | sat8(y)
+    uint32_t hi, w;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b), "r"(a), "r"(hi));
+    return w;
+}
 __device__ __forceinline__ int requant8_127f(float x, float kp, float half) {
     return max(-127, floor_sat_s8(__fadd_rd(__fmul_rn(kp, x), half)));
 }

@@ -276,6 +276,107 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
                                            pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
 }
 
+// Conv_P1, lean variant for K = 8 when the MAGIC epilogue is exact (host check: ayq.cu / magic_coeffs_ok):
+//   * the patch is read with 16-byte loads (4 pixels x 3 channels per work item) and quantised without conversions:
+//     rint(RN(x * s)) = low byte of the bits of RN(RN(x * s) + 1.5 * 2^23)  (|x * s| <= 127);
+//   * even and odd input columns live in separate shared arrays, so the stride-2 taps of a warp are stride-1 words
+//     (no bank conflicts);
+//   * the accumulators start at bias + 0x4B400000 and go straight into silu_magic (no I2F, no lower clamp).
+// Geometry: H = 2 Hout, W = 2 Wout, Wout % 32 == 0, Hout % 8 == 0 (checked by the host).  pc.i1 holds -k1p * C.
+template <bool U8>
+__global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc) {
+    __shared__ __align__(16) unsigned sE[2 * P1_TH + 1][P1_TW + 2];    // [r][j]     input x = 2 x0 + 2 j
+    __shared__ __align__(16) unsigned sO[2 * P1_TH + 1][P1_TW + 2];    // [r][j + 2] input x = 2 x0 + 2 j + 1   (j = -1: left halo)
+    __shared__ float2 lut2[AYQ_LUT256];
+    __shared__ unsigned qlut[U8 ? 256 : 1];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    pdl_trigger();
+    fill_lut256_magic(lut2, a.lut, a.M, tid, 256);
+    pdl_wait();                                                  // amax[] comes from the abs-max kernel
+    const float amax = a.amax[img];
+    const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);      // quant_matrix: scale(a, k) evaluated as reciprocal(a) * M
+    const bool any = amax > 0.f;
+    const size_t cs = (size_t)a.H * a.W;
+    const int iy0 = 2 * y0 - 1, ix0 = 2 * x0;
+    if (U8) {
+        qlut[tid] = any ? ((unsigned)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) & 0xffu) : 0u;
+        __syncthreads();
+    }
+    constexpr int ROWS = 2 * P1_TH + 1, GROUPS = P1_TW / 2;     // 17 rows x 16 groups of 4 input pixels
+    for (int i = tid; i < ROWS * GROUPS + ROWS; i += 256) {
+        if (i < ROWS * GROUPS) {
+            const int r = i / GROUPS, g = i - r * GROUPS;
+            const int iy = iy0 + r;
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+            if ((unsigned)iy < (unsigned)a.H && any) {
+                const size_t off = (size_t)img * 3 * cs + (size_t)iy * a.W + ix0 + 4 * g;
+                if (U8) {
+                    const unsigned c0 = __ldg((const unsigned*)(a.img_u8 + off)), c1 = __ldg((const unsigned*)(a.img_u8 + off + cs)),
+                                   c2 = __ldg((const unsigned*)(a.img_u8 + off + 2 * cs));
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        w[p] = qlut[(c0 >> (8 * p)) & 0xffu] | (qlut[(c1 >> (8 * p)) & 0xffu] << 8) | (qlut[(c2 >> (8 * p)) & 0xffu] << 16);
+                } else {
+                    const float4 v0 = __ldg((const float4*)(a.img + off)), v1 = __ldg((const float4*)(a.img + off + cs)),
+                                 v2 = __ldg((const float4*)(a.img + off + 2 * cs));
+                    const float f0[4] = {v0.x, v0.y, v0.z, v0.w}, f1[4] = {v1.x, v1.y, v1.z, v1.w}, f2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const unsigned z0 = __float_as_uint(__fadd_rn(__fmul_rn(f0[p], s), AYQ_MAGIC_F));
+                        const unsigned z1 = __float_as_uint(__fadd_rn(__fmul_rn(f1[p], s), AYQ_MAGIC_F));
+                        const unsigned z2 = __float_as_uint(__fadd_rn(__fmul_rn(f2[p], s), AYQ_MAGIC_F));
+                        w[p] = __byte_perm(__byte_perm(z0, z1, 0x0040), z2, 0x0410);   // (q0, q1, q2, q0): byte 3 meets a zero weight
+                    }
+                }
+            }
+            *(uint2*)&sE[r][2 * g] = make_uint2(w[0], w[2]);
+            *(uint2*)&sO[r][2 * g + 2] = make_uint2(w[1], w[3]);
+        } else {                                                  // left halo column x = 2 x0 - 1
+            const int r = i - ROWS * GROUPS;
+            const int iy = iy0 + r, ix = ix0 - 1;
+            unsigned wd = 0u;
+            if ((unsigned)iy < (unsigned)a.H && ix >= 0 && any) {
+                const size_t off = (size_t)img * 3 * cs + (size_t)iy * a.W + ix;
+                if (U8) {
+                    wd = qlut[__ldg(a.img_u8 + off)] | (qlut[__ldg(a.img_u8 + off + cs)] << 8) | (qlut[__ldg(a.img_u8 + off + 2 * cs)] << 16);
+                } else {
+                    const unsigned z0 = __float_as_uint(__fadd_rn(__fmul_rn(__ldg(a.img + off), s), AYQ_MAGIC_F));
+                    const unsigned z1 = __float_as_uint(__fadd_rn(__fmul_rn(__ldg(a.img + off + cs), s), AYQ_MAGIC_F));
+                    const unsigned z2 = __float_as_uint(__fadd_rn(__fmul_rn(__ldg(a.img + off + 2 * cs), s), AYQ_MAGIC_F));
+                    wd = __byte_perm(__byte_perm(z0, z1, 0x0040), z2, 0x0410);
+                }
+            }
+            sO[r][1] = wd;
+        }
+    }
+    __syncthreads();
+    const int tx = tid & (P1_TW - 1), ty = tid / P1_TW;
+    const int ox = x0 + tx, oy = y0 + ty;
+    int acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = pc.bias[j];             // bias + 0x4B400000 (host)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int vL = (int)sO[2 * ty + ky][tx + 1], vC = (int)sE[2 * ty + ky][tx], vR = (int)sO[2 * ty + ky][tx + 2];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc[j] = __dp4a(vL, (int)pc.w4[ky * 3][j], acc[j]);
+            acc[j] = __dp4a(vC, (int)pc.w4[ky * 3 + 1][j], acc[j]);
+            acc[j] = __dp4a(vR, (int)pc.w4[ky * 3 + 2][j], acc[j]);
+        }
+    }
+    const float half = a.half;
+    int r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = silu_magic(acc[j], pc.k1[j], pc.i1[j], pc.k2[j], lut2, half);
+    const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
+                                  (uint32_t)(oy >> 1) * (uint32_t)(a.Wout >> 1) + (uint32_t)(ox >> 1)
+                            : ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
+    *(uint4*)(a.out + (size_t)p * 16) = make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]),
+                                                   pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
+}
+
 // ---- per-image abs-max --------------------------------------------------------------------------------
 // grid (blocks, n); out[] must be zeroed first.  |x| >= 0 so the float bit pattern orders like an int.
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, float* __restrict__ out, size_t per_image) {
