@@ -228,6 +228,42 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         const uint32_t npix = (uint32_t)a.n * (uint32_t)a.Hout * (uint32_t)a.Wout;
         const uint32_t pix = ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
         const uint32_t off = ((uint32_t)(c0 >> 4) * npix + pix) * 16u;
+        if (EPI == 0 && FAST == 2 && a.gen_outs) {
+            // general output list.  A requantised copy (requantize(silu, old, new) with SCALAR coefficients, e.g. :741, :903) is
+            // a function of the 8-bit SiLU result alone: one byte load from the 256-entry table the prologue built with the
+            // very same requant8() arithmetic (smem right behind the sigmoid table).
+            const unsigned char* rq = (const unsigned char*)lut_s + AYQ_LUT256 * 8 + 128;
+            const uint4 vid = make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
+            for (int o = 0; o < a.nout; ++o) {
+                const OutSpec& os = a.out[o];
+                uint4 v = vid;
+                if (os.mode == 1) {
+                    const unsigned char* t = rq + 256 * o;
+                    uint32_t wd[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        wd[j] = (uint32_t)t[r[4 * j]] | ((uint32_t)t[r[4 * j + 1]] << 8) | ((uint32_t)t[r[4 * j + 2]] << 16) | ((uint32_t)t[r[4 * j + 3]] << 24);
+                    v = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                }
+                int8_t* base = (int8_t*)os.base;
+                if (os.up == 0) {
+                    *(uint4*)(base + off) = v;
+                } else if (os.up == 2) {
+                    const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
+                    const uint32_t plane = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)N >> 4) + (uint32_t)(c0 >> 4);
+                    *(uint4*)(base + (((plane * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u) = v;
+                } else {                 // 2x nearest upsample (:900, :935): 2x2 replicate
+                    const uint32_t W2 = (uint32_t)a.Wout * 2u;
+                    const uint32_t p00 = ((uint32_t)img * (uint32_t)a.Hout * 2u + 2u * (uint32_t)oy) * W2 + 2u * (uint32_t)ox;
+                    int8_t* pl = base + (uint32_t)(c0 >> 4) * npix * 64u;
+                    *(uint4*)(pl + p00 * 16u) = v;
+                    *(uint4*)(pl + (p00 + 1u) * 16u) = v;
+                    *(uint4*)(pl + (p00 + W2) * 16u) = v;
+                    *(uint4*)(pl + (p00 + W2 + 1u) * 16u) = v;
+                }
+            }
+            return;
+        }
         if (EPI != 2) {
             const uint4 v = FAST == 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
                                       : make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));

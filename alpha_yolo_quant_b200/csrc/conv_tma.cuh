@@ -23,6 +23,7 @@ namespace ayq {
 namespace tc {
 
 constexpr int TMA_MAX_MAPS = 8;
+#define AYQ_MAX_OUT_ 3
 constexpr int TMA_MAX_OPS = 56;
 constexpr int TMA_MAX_STAGES = 24;
 // block = 256 + 256 * EG threads: warps 0-1 MMA issuers, 2-5 TMA producers, 6-7 idle, then EG epilogue groups (4 warps) per pipeline
@@ -105,7 +106,16 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         }
         for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i] + (FAST == 2 ? AYQ_MAGIC_I : 0);
     }
-    if (EPI == 0 && FAST == 2) fill_lut256_magic((float2*)lut_s, a.lut, a.M, tid, TMA_THREADS);
+    if (EPI == 0 && FAST == 2) {
+        fill_lut256_magic((float2*)lut_s, a.lut, a.M, tid, TMA_THREADS);
+        if (a.gen_outs) {                                          // 256-byte table per requantised output: index = SiLU result + 128
+            unsigned char* rq = (unsigned char*)lut_s + AYQ_LUT256 * 8;
+            for (int i = tid; i < 256 * a.nout; i += TMA_THREADS) {
+                const OutSpec& os = a.out[i >> 8];
+                rq[i] = (unsigned char)(os.mode == 1 ? requant8((float)((i & 255) - 128), os.k, os.inv, a.M) : ((i & 255) - 128));
+            }
+        }
+    }
     else if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -320,6 +330,7 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     size_t smem = 0;
     unsigned grid = 0;
     int fast = 0;             // epilogue variant: 0 generic, 1 FAST (folded coefficients), 2 MAGIC (silu_magic)
+    int gen_outs = 0;         // MAGIC with a general output list
 };
 
 struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; };
@@ -423,9 +434,14 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.n = a.n; L.ok = 0;
     if (!s.ready) return 0;
     const int N = a.cout;
-    const bool fast = tma_fast(a);                                // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
-    const bool magic = fast && magic_epilogue_ok(a, h_tab, h_bias, h_lut, h_w, (a.nkc + 1) & ~1);
+    // MAGIC epilogue: any output list (32-bit store offsets: the largest output, 4x for an upsampled copy, stays below 4 GB)
+    bool any_up = false;
+    for (int o = 0; o < a.nout; ++o) any_up |= a.out[o].up == 1;
+    const bool magic = !a.acc_tap && (unsigned long long)a.n * a.cout * a.Hout * a.Wout * (any_up ? 4 : 1) < (1ull << 32) &&
+                       magic_epilogue_ok(a, h_tab, h_bias, h_lut, h_w, (a.nkc + 1) & ~1);
+    const bool fast = magic || tma_fast(a);                       // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
     L.fast = magic ? 2 : fast ? 1 : 0;
+    L.gen_outs = magic && !tma_fast(a) ? 1 : 0;                   // beyond "one identity output (+ phase-split copy)"
     if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, 0)) return 0;
     tc::TcParams& tp = L.tp;
     int bw_log = 4;
@@ -519,7 +535,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             pl.a_slot_bytes = (int)(((size_t)reg16 * 16 + 1023) & ~(size_t)1023);
             tp.KS = 2; tp.nst = 0; tp.lag = 0;
             tp.resident_b = 1;
-            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 : 0;        // float2 entries for the MAGIC epilogue
+            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 + 256 * AYQ_MAX_OUT_ : 0;   // float2 sigmoid table + requant byte tables (MAGIC epilogue)
             const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
             const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
             const size_t avail = (size_t)s.budget_kb * 1024 - fixed - w_bytes;
@@ -617,7 +633,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     }
     for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
     // shared memory budget
-    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 : 0;        // float2 entries for the MAGIC epilogue
+    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 + 256 * AYQ_MAX_OUT_ : 0;   // float2 sigmoid table + requant byte tables (MAGIC epilogue)
     const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = (size_t)s.budget_kb * 1024;
@@ -644,7 +660,9 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
 
 static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t st) {
     TmaKernel kern = tma_pick(a.cout, a.epi, L.fast);
-    return launch_k(kern, dim3(L.grid), dim3(a.cout <= TC_CT_MAXN ? 768 : 512), L.smem, st, a, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
+    ConvArgs a2 = a;
+    a2.gen_outs = L.gen_outs;
+    return launch_k(kern, dim3(L.grid), dim3(a.cout <= TC_CT_MAXN ? 768 : 512), L.smem, st, a2, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq

@@ -40,6 +40,7 @@ struct ConvArgs {
     int* acc_tap;               // NCHW int32 (n, cout, Hout, Wout) or nullptr
     float half;                 // 0.5f, kept in a register by the fast epilogues (see silu_q127)
     long long* dbg;             // AYQ_ROLE_PROF=1: per-CTA cycle counters of the warp roles [grid][16], else nullptr
+    int gen_outs;               // MAGIC epilogue only: 1 = general output list (requantised copies through 256-byte tables, upsample)
 };
 
 // byte offset of the 16-byte row (channels [c0, c0+16) of output pixel (img, oy, ox)) in a phase-split buffer

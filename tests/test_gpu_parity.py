@@ -279,3 +279,36 @@ def test_calibration_save_max_a():
         assert [float(v) for v in batched[name]] == ref[name]
     txt = cal.format_max_a_all(one)
     assert cal.parse_max_a_all(txt)['conv8'] == [round(v, 4) for v in ref['conv8']]
+
+
+def test_production_plan_intermediate_tensors_match_oracle(golden_dir):
+    """The production plan (no accumulator taps) is the one that runs the MAGIC epilogue, the requant byte tables, the
+    phase-split stores and the lean Conv_P1: every activation buffer it materialises must equal the oracle's tensor."""
+    from alpha_yolo_quant_b200 import plan as P
+    p, e = _setup(golden_dir, 8, taps=False, impl='tma')
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = Y.OracleYolov8(wl)
+    xs = _images([3, 202])
+    o.forward(xs.numpy(), trace=True)
+    tr = o.trace
+    e.forward(xs.cuda())
+    torch.cuda.synchronize()
+    silu_names = [nm for nm, _ in P.LAYERS if not nm.endswith('_2') or not (nm.startswith('x_') and ('up_2' in nm or 'down_2' in nm))]
+    assert len(silu_names) == 57 == len(tr['silu'])
+    checked = 0
+    for idx, nm in enumerate(silu_names):
+        meta = p.info['layers'][nm]
+        buf = meta.get('silu_buf', meta.get('ps_buf'))
+        if buf is None:
+            continue                                               # only requantised copies are stored (checked below)
+        got = e.export_buffer(buf, 2).cpu().numpy()
+        assert np.array_equal(got, tr['silu'][idx]), nm
+        checked += 1
+    for t, (nm, j) in enumerate(REQUANT_ORDER):
+        bufs = p.info['layers'][nm].get('requant_bufs', [])
+        if j < len(bufs):
+            got = e.export_buffer(bufs[j][0], 2).cpu().numpy()
+            assert np.array_equal(got, tr['requant'][t]), (nm, j)
+            checked += 1
+    assert checked >= 60, checked
+    e.close()
