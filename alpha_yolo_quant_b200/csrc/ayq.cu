@@ -74,6 +74,7 @@ struct ayq_engine {
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
     int fast_div = 0;                      // DFL division shortcut verified on this device (div_selfcheck_kernel)
+    bool p1_dp4a = false;                  // AYQ_P1_DP4A=1: keep Conv_P1 on the CUDA cores (conv_p1_fast_kernel) also when a tcgen05 conv family is selected
     bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
     long long* d_role = nullptr;
     TcState tc;                            // tcgen05 path state
@@ -212,6 +213,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
     e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
+    e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
     if (e->role_prof) {
         e->use_graph = false;
         cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
@@ -422,8 +424,18 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                           magic_coeffs_ok(16, a.M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
         if (lean) {                                                // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
             for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }
-            if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(a.Wout / P1_TW, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
-            else CK(launch_k(conv_p1_fast_kernel<false>, dim3(a.Wout / P1_TW, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
+            if (e->conv_impl >= 1 && !e->p1_dp4a) {                // tensor-core Conv_P1 (conv_tc.cuh): per-parity weight matrices with the byte shift
+                tc::P1B wb;
+                memset(&wb, 0, sizeof wb);
+                for (int par = 0; par < 2; ++par)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int co = 0; co < 16; ++co)
+                            for (int t = 0; t < 9; ++t)            // t = kx * 3 + c
+                                wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
+                if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true>, dim3(1, a.Hout / P1_TH, n), dim3(P1TC_THREADS), 0, st, a, pc, wb));
+                else CK(launch_k(tc::conv_p1_tc_kernel<false>, dim3(1, a.Hout / P1_TH, n), dim3(P1TC_THREADS), 0, st, a, pc, wb));
+            } else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
+            else CK(launch_k(conv_p1_fast_kernel<false>, dim3(1, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
         } else if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
         else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
         break;

@@ -135,6 +135,151 @@ __device__ __forceinline__ void tmem_ld_wait16(int* r) {
                  :: "memory");
 }
 
+// ---- Conv_P1 on the tensor cores -----------------------------------------------------------------------------------
+// Tile = 32 x 8 output pixels of one image, split by the parity of ox into two M = 128 GEMM tiles (row = ty * 16 + ox / 2).
+// The quantised patch is kept in shared memory as bytes, channel fastest: pixel j of a patch row at byte 4 + 3 j (the left
+// halo pixel at bytes 1..3).  For filter row ky the nine bytes an output pixel needs (3 taps x 3 channels) are CONTIGUOUS
+// there and start at byte 1 + 12 h (ox even) or 7 + 12 h (ox odd): the thread copies the three ALIGNED words that contain
+// them into its 16-byte A row, and the per-parity weight matrices carry the byte shift (positions 1..9 or 3..11, zero
+// elsewhere), so the im2col is three word copies per filter row - no byte shuffling.  K = 3 chunks (one per ky) + one
+// zero-weight chunk: MMA 1 = chunks (ky0, ky1), MMA 2 = chunks (ky2, ky0 x zero weights).
+struct P1B { int8_t b[2][4][16][16]; };    // [ox parity][ky2, zero, ky0, ky1][cout][byte position]
+
+#define P1TC_THREADS 288          // warps 0-7: one output pixel each (im2col row, TMEM lane, epilogue); all 9 warps: patch loaders
+template <bool U8>
+__global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc,
+                                                                const __grid_constant__ P1B wb) {
+    __shared__ __align__(1024) unsigned char sA[2][3][2048];      // [parity][ky2, ky0, ky1][128 rows][16 B]
+    __shared__ __align__(128) unsigned char sB[2][4][256];
+    __shared__ __align__(16) unsigned sQ[2 * P1_TH + 1][56];       // 224-byte rows (conflict-free word stride 3 across a half warp)
+    __shared__ float2 lut2[AYQ_LUT256];
+    __shared__ unsigned qlut[U8 ? 256 : 1];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    pdl_trigger();
+    fill_lut256_magic(lut2, a.lut, a.M, tid, P1TC_THREADS);
+    if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_wait();                                                   // amax[] comes from the abs-max kernel
+    const float amax = a.amax[img];
+    const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);
+    const bool any = amax > 0.f;
+    const size_t cs = (size_t)a.H * a.W;
+    if (U8 && tid < 256) qlut[tid] = any ? ((unsigned)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) & 0xffu) : 0u;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    // patch loader: thread -> (patch row lr, group of 4 input pixels lg); 17 x 16 = 272 work items, one per thread.  The next
+    // tile's 48 bytes are fetched into registers while this tile is multiplied and post-processed.  The left halo pixel of a
+    // tile is pixel 63 of the previous tile's patch (zero padding for the first), carried in a register by the lg = 15 thread.
+    constexpr int ROWS = 2 * P1_TH + 1, GROUPS = P1_TW / 2;
+    const bool loader = tid < ROWS * GROUPS;
+    const int lr = tid / GROUPS, lg = tid - lr * GROUPS;
+    const int liy = 2 * y0 - 1 + lr;
+    const bool lvalid = loader && (unsigned)liy < (unsigned)a.H && any;
+    const size_t lbase = (size_t)img * 3 * cs + (size_t)(lvalid ? liy : 0) * a.W + 4 * lg;
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0, pf2 = pf0;
+    unsigned pu0 = 0u, pu1 = 0u, pu2 = 0u;
+    if (lvalid) {
+        if (U8) { pu0 = __ldg((const unsigned*)(a.img_u8 + lbase)); pu1 = __ldg((const unsigned*)(a.img_u8 + lbase + cs)); pu2 = __ldg((const unsigned*)(a.img_u8 + lbase + 2 * cs)); }
+        else { pf0 = __ldg((const float4*)(a.img + lbase)); pf1 = __ldg((const float4*)(a.img + lbase + cs)); pf2 = __ldg((const float4*)(a.img + lbase + 2 * cs)); }
+    }
+    unsigned carry = 0u;
+    uint32_t phase = 0;
+    const int e = (tid >> 7) & 1, row = tid & 127, ty = row >> 4, h = row & 15;
+    // one CTA walks the whole band of x tiles: tables, weights, TMEM allocation and barrier are set up once per band
+    for (int x0 = 0; x0 < a.Wout; x0 += P1_TW) {
+        if (loader) {
+            unsigned w0 = 0u, w1 = 0u, w2 = 0u;
+            if (lvalid) {
+                unsigned q[3][4];                                  // [channel][pixel], value in byte 0
+                if (U8) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        q[0][p] = qlut[(pu0 >> (8 * p)) & 0xffu]; q[1][p] = qlut[(pu1 >> (8 * p)) & 0xffu]; q[2][p] = qlut[(pu2 >> (8 * p)) & 0xffu];
+                    }
+                } else {
+                    const float f[3][4] = {{pf0.x, pf0.y, pf0.z, pf0.w}, {pf1.x, pf1.y, pf1.z, pf1.w}, {pf2.x, pf2.y, pf2.z, pf2.w}};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) q[c][p] = __float_as_uint(__fadd_rn(__fmul_rn(f[c][p], s), AYQ_MAGIC_F));
+                }
+                // 12 bytes, channel fastest: (p0c0 p0c1 p0c2 p1c0) (p1c1 p1c2 p2c0 p2c1) (p2c2 p3c0 p3c1 p3c2)
+                w0 = __byte_perm(__byte_perm(q[0][0], q[1][0], 0x0040), __byte_perm(q[2][0], q[0][1], 0x0040), 0x5410);
+                w1 = __byte_perm(__byte_perm(q[1][1], q[2][1], 0x0040), __byte_perm(q[0][2], q[1][2], 0x0040), 0x5410);
+                w2 = __byte_perm(__byte_perm(q[2][2], q[0][3], 0x0040), __byte_perm(q[1][3], q[2][3], 0x0040), 0x5410);
+            }
+            sQ[lr][1 + 3 * lg] = w0; sQ[lr][2 + 3 * lg] = w1; sQ[lr][3 + 3 * lg] = w2;
+            if (lg == GROUPS - 1) { sQ[lr][0] = carry; carry = w2 & 0xffffff00u; }    // halo pixel -> bytes 1..3 of word 0
+        }
+        __syncthreads();
+        if (lvalid && x0 + P1_TW < a.Wout) {                      // next tile's pixels: in flight during the rest of this iteration
+            const size_t o = lbase + 2 * (x0 + P1_TW);
+            if (U8) { pu0 = __ldg((const unsigned*)(a.img_u8 + o)); pu1 = __ldg((const unsigned*)(a.img_u8 + o + cs)); pu2 = __ldg((const unsigned*)(a.img_u8 + o + 2 * cs)); }
+            else { pf0 = __ldg((const float4*)(a.img + o)); pf1 = __ldg((const float4*)(a.img + o + cs)); pf2 = __ldg((const float4*)(a.img + o + 2 * cs)); }
+        }
+        if (warp < 8) {                                           // im2col: three aligned words per filter row
+            const int wi = 3 * h + e;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const unsigned* src = &sQ[2 * ty + ky][wi];
+                const unsigned w0 = src[0], w1 = src[1], w2 = src[2];
+                *(uint4*)&sA[e][ky == 2 ? 0 : ky + 1][row * 16] = make_uint4(w0, w1, w2, w2);   // byte positions 12..15 meet zero weights
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_i8(16);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t dcol = tmem_base + (uint32_t)(t * 16);
+                mma_i8(dcol, make_desc(smem_u32(&sA[t][1][0]), 2048, 128), make_desc(smem_u32(&sB[t][2][0]), 256, 128), idesc, 0u);   // ky0, ky1
+                mma_i8(dcol, make_desc(smem_u32(&sA[t][0][0]), 2048, 128), make_desc(smem_u32(&sB[t][0][0]), 256, 128), idesc, 1u);   // ky2, (ky0 x 0)
+            }
+            mma_commit(smem_u32(&bar));
+        }
+        __syncwarp();
+        if (warp < 8) {
+            mbar_wait(smem_u32(&bar), phase);
+            tc_fence_after();
+            int acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(e * 16), acc);
+            tmem_ld_wait16(acc);
+            const float half = a.half;
+            int r[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = silu_magic(acc[j] + pc.bias[j], pc.k1[j], pc.i1[j], pc.k2[j], lut2, half);
+            const int ox = x0 + 2 * h + e, oy = y0 + ty;
+            const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
+                                          (uint32_t)(oy >> 1) * (uint32_t)(a.Wout >> 1) + (uint32_t)(ox >> 1)
+                                    : ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
+            *(uint4*)(a.out + (size_t)p * 16) = make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]),
+                                                           pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
+        }
+        phase ^= 1u;
+        tc_fence_before();
+        __syncthreads();                                          // accumulators read, patch consumed: the next tile may overwrite both
+        tc_fence_after();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    }
+}
+
 struct TcParams {
     int KS;            // K chunks per stage (even)
     int NS;            // stages in the A ring

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant
     __shared__ float2 lut2[AYQ_LUT256];
     __shared__ unsigned qlut[U8 ? 256 : 1];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z;
     pdl_trigger();
     fill_lut256_magic(lut2, a.lut, a.M, tid, 256);
     pdl_wait();                                                  // amax[] comes from the abs-max kernel
@@ -299,12 +299,13 @@ __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant
     const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);      // quant_matrix: scale(a, k) evaluated as reciprocal(a) * M
     const bool any = amax > 0.f;
     const size_t cs = (size_t)a.H * a.W;
-    const int iy0 = 2 * y0 - 1, ix0 = 2 * x0;
-    if (U8) {
-        qlut[tid] = any ? ((unsigned)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) & 0xffu) : 0u;
-        __syncthreads();
-    }
+    const int iy0 = 2 * y0 - 1;
+    if (U8) qlut[tid] = any ? ((unsigned)__float2int_rn(__fmul_rn(__fdiv_rn((float)tid, 255.f), s)) & 0xffu) : 0u;
     constexpr int ROWS = 2 * P1_TH + 1, GROUPS = P1_TW / 2;     // 17 rows x 16 groups of 4 input pixels
+    // one CTA walks the whole band of x tiles: the prologue (tables, scale) is paid once per band
+    for (int x0 = 0; x0 < a.Wout; x0 += P1_TW) {
+    const int ix0 = 2 * x0;
+    __syncthreads();                                             // previous tile's taps are consumed (first pass: qlut / lut2 visible)
     for (int i = tid; i < ROWS * GROUPS + ROWS; i += 256) {
         if (i < ROWS * GROUPS) {
             const int r = i / GROUPS, g = i - r * GROUPS;
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant
                             : ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
     *(uint4*)(a.out + (size_t)p * 16) = make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]),
                                                    pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
+    }
 }
 
 // ---- per-image abs-max --------------------------------------------------------------------------------
