@@ -380,6 +380,60 @@ def capture_goldens_float(work, pkg_root, k, images_u8):
     return out
 
 
+def capture_weight_quant(work, pkg_root, k, layers):
+    """Run the UNMODIFIED stage_6_full_quant.py (text dumps silenced exactly as in run_pipeline) under a profile hook and
+    record, for the chosen layers, the arguments and results of conv_quant() (stage_6_full_quant.py:89-126):
+    float weights / bias, scale_input, start -> integer weights, integer bias, per-channel scale_res."""
+    import importlib
+    sw = importlib.import_module('yolov8n_quantisation.quantisation.utils.save_weights')
+    cp = importlib.import_module('yolov8n_quantisation.quantisation.utils.conv2d_print_fp')
+    rt = importlib.import_module('yolov8n_quantisation.quantisation.utils.result_txt')
+    noop = lambda *a, **kw: None
+    for mod in (sw, cp, rt):
+        for nm in dir(mod):
+            if nm.startswith('save_txt') or nm in ('conv2d', 'result_txt', 'add_rescale_shift', 'add_silu'):
+                setattr(mod, nm, noop)
+    out = {}
+    pending = {}
+
+    def prof(frame, event, arg):
+        if frame.f_code.co_name != 'conv_quant':
+            return
+        if event == 'call':
+            loc = frame.f_locals
+            name = loc['layer_name']
+            if name in layers:
+                pending[id(frame)] = (name, np.array(loc['conv'], copy=True), np.array(loc['bias_conv'], copy=True),
+                                      np.float64(loc['scale_input']) if np.ndim(loc['scale_input']) == 0 else np.array(loc['scale_input'], np.float64),
+                                      bool(loc['start']))
+        elif event == 'return' and id(frame) in pending:
+            name, w, b, si, start = pending.pop(id(frame))
+            loc = frame.f_locals
+            out[f'{name}/w'] = w
+            out[f'{name}/w_dtype'] = np.array(str(w.dtype))
+            out[f'{name}/b'] = b
+            out[f'{name}/b_dtype'] = np.array(str(b.dtype))
+            out[f'{name}/scale_input'] = np.asarray(si, np.float64)
+            out[f'{name}/scale_input_type'] = np.array(str(type(loc['scale_input'])))
+            out[f'{name}/start'] = np.array(start)
+            out[f'{name}/qw'] = np.asarray(loc['conv']).astype(np.int8)
+            out[f'{name}/qb'] = np.asarray(loc['bias']).astype(np.int64)
+            out[f'{name}/scale_res'] = np.asarray(loc['scale_res'], np.float64)
+            out[f'{name}/scale_res_dtype'] = np.array(str(np.asarray(loc['scale_res']).dtype))
+
+    real_sleep = time.sleep
+    time.sleep = noop
+    sys.setprofile(prof)
+    try:
+        run_stage(pkg_root, 'stage_6_full_quant.py')
+    finally:
+        sys.setprofile(None)
+        time.sleep = real_sleep
+    out['layers'] = np.array(sorted(set(kk.split('/')[0] for kk in out)))
+    out['versions'] = np.array(f'numpy {np.__version__}')
+    return out
+
+
 def export_workload(work, k, g):
     """Pack what the hot path reads from disk into one small npz."""
     main_dir = f'{k}_nano'
@@ -413,6 +467,8 @@ def main():
     ap.add_argument('--n-golden', type=int, default=12)
     ap.add_argument('--dump', default=None, help='scratch dir for full per-layer tensors (not committed)')
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
+    ap.add_argument('--weight-quant', default='', metavar='LAYERS',
+                    help='only record conv_quant() goldens of stage_6_full_quant.py for these comma-separated layers')
     ap.add_argument('--float-head', type=int, default=0, metavar='N',
                     help='only record stage_8_torch.py (float head) goldens for N images -> golden_float_k{K}.npz')
     args = ap.parse_args()
@@ -432,6 +488,11 @@ def main():
     install_stubs(calib)
     if not args.skip_pipeline:
         run_pipeline(work, pkg_root, k)
+    if args.weight_quant:
+        gold = capture_weight_quant(work, pkg_root, k, set(args.weight_quant.split(',')))
+        np.savez_compressed(os.path.join(args.out, f'golden_wquant_k{k}.npz'), **gold)
+        print('[harness] wrote weight-quantiser goldens:', list(gold['layers']))
+        return
     if args.float_head:
         images = [synth.synth_image_u8(s) for s in range(args.float_head)]
         gold = capture_goldens_float(work, pkg_root, k, images)
