@@ -756,6 +756,15 @@ extern "C" int ayq_quant_input_f32(const float* x, float* y, float* amax, float*
     CK(cudaGetLastError());
     return 0;
 }
+extern "C" int ayq_quant_weights_f32(const float* w, const float* bias, int cout, size_t per_channel, int bits, double scale_input,
+                                     int8_t* qw, int64_t* qb, double* scale_res, void* stream) {
+    if (!w || !bias || !qw || !qb || !scale_res || cout < 0 || bits < 2 || bits > 8) return fail(-22, "ayq_quant_weights_f32: bad arguments (bits 2..8)");
+    if (!cout || !per_channel) return 0;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    quant_weights_kernel<<<cout, 256, 0, (cudaStream_t)stream>>>(w, bias, per_channel, (1 << (bits - 1)) - 1, scale_input, qw, (long long*)qb, scale_res);
+    CK(cudaGetLastError());
+    return 0;
+}
 extern "C" int ayq_nms(ayq_handle e, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream) {
     if (!e || !dbox_cls || !dets || !counts || n < 0) return fail(-22, "ayq_nms: bad arguments");
     if (!n) return 0;

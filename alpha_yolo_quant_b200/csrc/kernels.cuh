@@ -1117,6 +1117,37 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_float_kernel(const NmsFloatAr
     }
 }
 
+// ---- weight quantiser: conv_quant() of stage_6_full_quant.py:89-126 ---------------------------
+// grid (cout), block 256.  Per output channel: a = max|w|, s = fl32(M / a), q = rint(fl32(w * s)) (utils/quant_matrix.py:56-78,
+// float32 arithmetic as numpy >= 2 evaluates it); bias_q = trunc(double(b) * (scale_input * double(s))) (utils/quant_bias.py:2-4,
+// float64); scale_res = scale_input * double(s) (:93-96, :122).  An all-zero channel gives q = 0, scale = +inf.
+__global__ void __launch_bounds__(256) quant_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, size_t per_channel,
+                                                            int M, double scale_input, int8_t* __restrict__ qw, long long* __restrict__ qb,
+                                                            double* __restrict__ scale_res) {
+    __shared__ float red[8];
+    __shared__ float s_sh;
+    const int c = blockIdx.x;
+    const float* wc = w + (size_t)c * per_channel;
+    float m = 0.f;
+    for (size_t i = threadIdx.x; i < per_channel; i += 256) m = fmaxf(m, fabsf(wc[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        const float s = __fdiv_rn((float)M, m);
+        s_sh = s;
+        const double bs = __dmul_rn(scale_input, (double)s);
+        scale_res[c] = bs;
+        qb[c] = m > 0.f ? (long long)__dmul_rn((double)bias[c], bs) : 0ll;
+    }
+    __syncthreads();
+    const float s = s_sh;
+    for (size_t i = threadIdx.x; i < per_channel; i += 256)
+        qw[(size_t)c * per_channel + i] = isfinite(s) ? (int8_t)__float2int_rn(__fmul_rn(wc[i], s)) : (int8_t)0;
+}
+
 // ---- export a plane buffer as NCHW int32 (parity taps) ------------------------------------------------
 __global__ void export_planes_kernel(const void* __restrict__ src, int elem_bytes, int nplanes, int n, int H, int W, int* __restrict__ dst) {
     const size_t total = (size_t)n * nplanes * 16 * H * W;

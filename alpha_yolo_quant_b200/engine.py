@@ -42,6 +42,7 @@ SIGNATURES = {
     'ayq_nms': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'ayq_nms_boxes': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'ayq_coord_float': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    'ayq_quant_weights_f32': (_int, [_vp, _vp, _int, _sz, _int, _c.c_double, _vp, _vp, _vp, _vp]),
 }
 
 _LIB = None

@@ -90,6 +90,13 @@ int ayq_lut_f32(const float* x, float* y, const float* lut, int key_min, int key
 int ayq_quant_input_f32(const float* x, float* y, float* amax, float* scales, int n, size_t per_image, int bits, void* stream);
 /* save_max_a(), utils/save_a.py:11-26: out[i] = max|x[i, :]| over per_image floats (calibration taps). */
 int ayq_absmax_f32(const float* x, float* out, int n, size_t per_image, void* stream);
+/* conv_quant() of stage_6_full_quant.py:89-126 without its text dumps (the producer of the stage_7 weights):
+ * per output channel a = max|w|, s = fl32((2^(bits-1)-1) / a), qw = rint(fl32(w * s)) (utils/quant_matrix.py:56-78);
+ * qb = trunc(double(bias) * (scale_input * s)) (utils/quant_bias.py:2-4); scale_res = scale_input * s (:93-96,:122; the first
+ * layer passes scale_input = 2^(bits-1)-1, `start=True`).  w device float32 (cout, per_channel), bias device float32 (cout),
+ * qw device int8 (cout, per_channel), qb device int64 (cout), scale_res device float64 (cout). */
+int ayq_quant_weights_f32(const float* w, const float* bias, int cout, size_t per_channel, int bits, double scale_input,
+                          int8_t* qw, int64_t* qb, double* scale_res, void* stream);
 /* coord_quant() + nms_quant() + scale_boxes/clip_boxes (stage_8_torch_full_quant.py:248-423) on a
  * caller-provided prediction tensor: dbox_cls device float32 (n,84,8400). */
 int ayq_nms(ayq_handle h, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream);

@@ -132,3 +132,17 @@ def test_float_nms_restatement_against_torchvision():
         keep = FH.nms_greedy(boxes, scores, 0.45)
         ref = tv.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.45).numpy()
         assert np.array_equal(keep, ref), n
+
+
+# ---- weight quantiser, oracle/weight_quant.py ---------------------------------------------------
+def test_weight_quant_oracle_matches_reference(golden_dir):
+    """golden_wquant_k8.npz: arguments and results of the reference's conv_quant() for seven layers (first layer with
+    start=True, 3x3 / 1x1 convs, the 16-bit class-branch layer), recorded from the unmodified stage_6_full_quant.py."""
+    from oracle import weight_quant as WQ
+    g = np.load(os.path.join(golden_dir, 'golden_wquant_k8.npz'))
+    assert len(g['layers']) == 7
+    for l in g['layers']:
+        q, b, s = WQ.conv_quant(g[f'{l}/w'], g[f'{l}/b'], float(g[f'{l}/scale_input']), 8, bool(g[f'{l}/start']))
+        assert np.array_equal(q, g[f'{l}/qw'].astype(np.int64)), l
+        assert np.array_equal(b, g[f'{l}/qb']), l
+        assert np.array_equal(s, g[f'{l}/scale_res']), l
