@@ -33,22 +33,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // try_wait suspends the thread in hardware until the phase completes or the time hint expires.  A wait that lasts
-    // longer than ~2 s of SM clock can only be a protocol bug: trap (reported as a launch failure) instead of hanging
-    // the GPU.
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (int it = 0;; ++it) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (it == 64) t0 = clock64();
-        if (it > 64 && (it & 63) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    // try_wait suspends the thread in hardware until the phase completes or the time hint expires.  The retry loop is kept
+    // to a probe, a counter and a branch (it runs a dozen times per tile in every waiting warp and competes with the
+    // epilogue warps for issue slots); ~2^27 failed probes (seconds) can only be a protocol bug: trap (reported as a launch
+    // failure) instead of hanging the GPU.
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t it = 0;; ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        if (it > (1u << 27)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
