@@ -74,6 +74,7 @@ struct ayq_engine {
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
     int fast_div = 0;                      // DFL division shortcut verified on this device (div_selfcheck_kernel)
+    int p1_chunk = 0;                      // AYQ_P1_CHUNK: images per abs-max -> Conv_P1 chunk (fp32 device input), 0 = whole pass
     bool p1_dp4a = false;                  // AYQ_P1_DP4A=1: keep Conv_P1 on the CUDA cores (conv_p1_fast_kernel) also when a tcgen05 conv family is selected
     bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
     long long* d_role = nullptr;
@@ -214,6 +215,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
     e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
+    if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (e->role_prof) {
         e->use_graph = false;
         cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
@@ -379,7 +381,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     return 0;
 }
 
-struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; };
+struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; };
 
 // launch plan op i of a pass
 static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t st) {
@@ -402,6 +404,8 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;
         a.half = 0.5f;
         a.ps = f[P1_OUT_PS];
+        a.img0 = pa.p1_img0;
+        const int nz = pa.p1_cnt >= 0 ? pa.p1_cnt : n;                // images of this launch (chunked abs-max -> Conv_P1 interleave)
         const bool fold = a.M == 127;                              // K = 8: the kernel takes folded coefficients k * 2^-s (exact)
         P1Const pc;
         const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
@@ -432,12 +436,12 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                         for (int co = 0; co < 16; ++co)
                             for (int t = 0; t < 9; ++t)            // t = kx * 3 + c
                                 wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
-                if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true>, dim3(1, a.Hout / P1_TH, n), dim3(P1TC_THREADS), 0, st, a, pc, wb));
-                else CK(launch_k(tc::conv_p1_tc_kernel<false>, dim3(1, a.Hout / P1_TH, n), dim3(P1TC_THREADS), 0, st, a, pc, wb));
-            } else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
-            else CK(launch_k(conv_p1_fast_kernel<false>, dim3(1, a.Hout / P1_TH, n), dim3(256), 0, st, a, pc));
-        } else if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
-        else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, n), dim3(256), 0, st, a, pc));
+                if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
+                else CK(launch_k(tc::conv_p1_tc_kernel<false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
+            } else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
+            else CK(launch_k(conv_p1_fast_kernel<false>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
+        } else if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, nz), dim3(256), 0, st, a, pc));
+        else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, nz), dim3(256), 0, st, a, pc));
         break;
     }
     case OP_CONV: {
@@ -526,8 +530,22 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     int pe = 0;
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
-    if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
+    // The image is read twice (per-image abs-max, then quantise + Conv_P1).  With fp32 images a pass does not fit the L2, so
+    // the two kernels are interleaved over chunks of p1_chunk images: the second read of a chunk then comes from the L2.
+    const int chunk = (!prof && !e->debug_sync && !img_u8 && e->p1_chunk > 0 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1) ? e->p1_chunk : 0;
+    if (chunk && n > chunk) {
+        const size_t per = (size_t)3 * H * W;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = n - i0 < chunk ? n - i0 : chunk;
+            CK(launch_k(absmax_kernel, dim3(64, m), dim3(256), 0, st, img + (size_t)i0 * per, amax + i0, per));
+            pa.p1_img0 = i0; pa.p1_cnt = m;
+            int rc = launch_op(e, 0, pa, st);
+            if (rc) return rc;
+        }
+        pa.p1_img0 = 0; pa.p1_cnt = -1;
+    } else if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
     else CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
+    const size_t op_first = (chunk && n > chunk) ? 1 : 0;            // Conv_P1 already launched chunk by chunk
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
     if (e->debug_sync) {
         cudaError_t de = cudaStreamSynchronize(st);
@@ -541,7 +559,7 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     bool graphable = e->use_graph && !prof && !e->debug_sync && !dbox_cls && e->conv_impl == 2 && g1 > g0;
     for (size_t i = g0; i < g1 && graphable; ++i)
         if (e->ops[i].f[0] == OP_CONV_P1 || e->ops[i].f[0] == OP_NMS || e->ops[i].f[0] == OP_NMS_FLOAT) graphable = false;
-    for (size_t i = 0; i < nops; ++i) {
+    for (size_t i = op_first; i < nops; ++i) {
         if (graphable && i == g0) {
             auto it = e->graphs.find(n);
             if (it == e->graphs.end()) {

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z + a.img0;
     pdl_trigger();
     fill_lut256_magic(lut2, a.lut, a.M, tid, P1TC_THREADS);
     if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];

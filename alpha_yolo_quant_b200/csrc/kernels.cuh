@@ -186,6 +186,7 @@ struct P1Args {
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
     int* acc_tap;
     float half;                 // 0.5f in a register (see silu_q127f)
+    int img0;                   // first image of this launch (grid.z counts from here); n stays the pass size (phase-split strides)
     int ps;                     // 1: phase-split output [(y&1)*2+(x&1)][n][Hout/2][Wout/2][16] (input layout of the stride-2 Conv_P2)
 };
 // weights and per-channel epilogue coefficients as a __grid_constant__ parameter: every use below has a compile-time
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
     __shared__ unsigned char qlut[256];                          // U8: quantised value of every byte, q = rint(fl32(fl32(v / 255) * s))
     __shared__ float lut_s[AYQ_LUT256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    const int x0 = blockIdx.x * P1_TW, y0 = blockIdx.y * P1_TH, img = blockIdx.z + a.img0;
     pdl_trigger();
     fill_lut256(lut_s, a.lut, a.M, tid, 256);
     pdl_wait();                                                  // amax[] comes from the abs-max kernel
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant
     __shared__ float2 lut2[AYQ_LUT256];
     __shared__ unsigned qlut[U8 ? 256 : 1];
     const int tid = threadIdx.x;
-    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z;
+    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z + a.img0;
     pdl_trigger();
     fill_lut256_magic(lut2, a.lut, a.M, tid, 256);
     pdl_wait();                                                  // amax[] comes from the abs-max kernel
