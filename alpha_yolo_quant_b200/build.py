@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libayq.so')
 STAMP = os.path.join(HERE, '.libayq.stamp')
+LIB_PROF = os.path.join(HERE, 'libayq_prof.so')        # same sources with -DAYQ_ROLE_PROF_BUILD (role-level cycle counters)
+STAMP_PROF = os.path.join(HERE, '.libayq_prof.stamp')
 SOURCES = ['ayq.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--fmad=false',            # the reference multiplies and adds in separate fp32 ops (SURVEY hard part 1)
@@ -37,21 +39,23 @@ def nvcc_path():
     return 'nvcc'
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, prof=False):
+    """prof=True builds the profiling variant libayq_prof.so (AYQ_ROLE_PROF=1 loads it instead of libayq.so)."""
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
+    lib, stamp = (LIB_PROF, STAMP_PROF) if prof else (LIB, STAMP)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return lib
+    cmd = [nvcc_path()] + NVCC_FLAGS + (['-DAYQ_ROLE_PROF_BUILD'] if prof else []) + (['-Xptxas', '-v'] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ['-o', lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    with open(STAMP, 'w') as f:
+    with open(stamp, 'w') as f:
         f.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, prof='--prof' in sys.argv))

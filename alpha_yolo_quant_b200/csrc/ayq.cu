@@ -214,6 +214,9 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
     e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
+#ifndef AYQ_ROLE_PROF_BUILD
+    if (e->role_prof) { delete e; return fail(-22, "AYQ_ROLE_PROF=1 needs the profiling build of the library (libayq_prof.so: python -m alpha_yolo_quant_b200.build --prof)"); }
+#endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (e->role_prof) {

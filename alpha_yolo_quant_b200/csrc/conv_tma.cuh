@@ -22,6 +22,16 @@ namespace ayq {
 
 namespace tc {
 
+// Role-level cycle counters (AYQ_ROLE_PROF=1) exist only in the profiling build of the library (libayq_prof.so, built with
+// -DAYQ_ROLE_PROF_BUILD): a predicated-off clock read still costs an issue slot, and these sit in every per-tile loop.
+#ifdef AYQ_ROLE_PROF_BUILD
+#define AYQ_DBG(a) ((a).dbg != nullptr)
+#define AYQ_CLK(a) ((a).dbg ? clock64() : 0)
+#else
+#define AYQ_DBG(a) false
+#define AYQ_CLK(a) 0ll
+#endif
+
 constexpr int TMA_MAX_MAPS = 8;
 #define AYQ_MAX_OUT_ 3
 constexpr int TMA_MAX_OPS = 56;
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         const int slot0 = m * NSH;
         int slot = 0, turn = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
-        long long d_wait = 0, d_t0 = a.dbg ? clock64() : 0;
+        long long d_wait = 0, d_t0 = AYQ_CLK(a);
         for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
@@ -169,9 +179,9 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 if (turn == q) {
                     const TmaStage sg = pl.st[s];
                     const int gs = slot0 + slot;
-                    const long long w0 = a.dbg ? clock64() : 0;
+                    const long long w0 = AYQ_CLK(a);
                     mbar_wait(empty0 + 8 * gs, ephase);
-                    if (a.dbg) d_wait += clock64() - w0;
+                    if (AYQ_DBG(a)) d_wait += clock64() - w0;
                     if (elect_one()) {
                         const uint32_t bar = full0 + 8 * gs;
                         const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 if (++slot == NSH) { slot = 0; ephase ^= 1; }
             }
         }
-        if (a.dbg && lane == 0 && q == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
+        if (AYQ_DBG(a) && lane == 0 && q == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
     } else if (warp < 2) {
         // ===== MMA issuer of pipeline m: warp-uniform control flow, one elected lane issues; the descriptor low words
         // (address | LBO) are stepped with 32-bit adds =====
@@ -209,11 +219,11 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         const int slot0 = m * NSH;
         int slot = 0, buf = 0;
         uint32_t fphase = 0, ephase = 3;                           // bit buf = parity to wait for on tempty[m][buf]; fresh barriers pass parity 1
-        long long d_we = 0, d_wf = 0, d_t0 = a.dbg ? clock64() : 0;
+        long long d_we = 0, d_wf = 0, d_t0 = AYQ_CLK(a);
         for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
-            const long long w0 = a.dbg ? clock64() : 0;
+            const long long w0 = AYQ_CLK(a);
             mbar_wait(tempty0 + 8 * (2 * m + buf), (ephase >> buf) & 1u);
-            if (a.dbg) d_we += clock64() - w0;
+            if (AYQ_DBG(a)) d_we += clock64() - w0;
             ephase ^= 1u << buf;
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)((m * nbuf + buf) * N);
@@ -222,9 +232,9 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 TmaStage sg = sg0;
                 if (s > 0) sg = pl.st[s];
                 const int gs = slot0 + slot;
-                const long long w1 = a.dbg ? clock64() : 0;
+                const long long w1 = AYQ_CLK(a);
                 mbar_wait(full0 + 8 * gs, fphase);
-                if (a.dbg) d_wf += clock64() - w1;
+                if (AYQ_DBG(a)) d_wf += clock64() - w1;
                 tc_fence_after();
                 if (elect_one()) {
                     uint32_t acc = accum;
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             }
             if (nbuf == 2) buf ^= 1;
         }
-        if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
+        if (AYQ_DBG(a) && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int gq = (warp - 8) >> 2;
@@ -265,17 +275,17 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         const uint32_t lane_quad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tphase = 0;                                     // bit buf = parity to wait for on tfull[grp][buf]
         int buf = EG == 2 ? (gq & 1) : 0;
-        long long d_wt = 0, d_t0 = a.dbg ? clock64() : 0;
+        long long d_wt = 0, d_t0 = AYQ_CLK(a);
         for (int t = blockIdx.x + (grp + 2 * (EG == 2 ? (gq & 1) : 0)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
             const uint32_t tfull_b = tfull0 + 8 * (2 * grp + buf), tempty_b = tempty0 + 8 * (2 * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
-            const long long w0 = a.dbg ? clock64() : 0;
+            const long long w0 = AYQ_CLK(a);
             mbar_wait(tfull_b, (tphase >> buf) & 1u);
             tphase ^= 1u << buf;
-            if (a.dbg) d_wt += clock64() - w0;
+            if (AYQ_DBG(a)) d_wt += clock64() - w0;
             tc_fence_after();
             int accA[16], accB[16];
             tmem_ld16(lane_base, accA);
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             }
             if (EG == 1 && nbuf == 2) buf ^= 1;
         }
-        if (a.dbg && (warp & 3) == 0 && lane == 0 && gq < 2) { a.dbg[blockIdx.x * 16 + 12 + 2 * gq] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * gq] = d_wt; }
+        if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gq < 2) { a.dbg[blockIdx.x * 16 + 12 + 2 * gq] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * gq] = d_wt; }
     }
     tc_fence_before();
     __syncthreads();
