@@ -74,6 +74,7 @@ struct ayq_engine {
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
     int fast_div = 0;                      // DFL division shortcut verified on this device (div_selfcheck_kernel)
+    int host_pass = 0, host_ramp = 0;      // AYQ_HOST_PASS: pass size of the host pipeline (default 64); AYQ_HOST_RAMP=1: smaller passes at both ends
     int p1_chunk = 0;                      // AYQ_P1_CHUNK: images per abs-max -> Conv_P1 chunk (fp32 device input), 0 = whole pass
     bool p1_dp4a = false;                  // AYQ_P1_DP4A=1: keep Conv_P1 on the CUDA cores (conv_p1_fast_kernel) also when a tcgen05 conv family is selected
     bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
@@ -219,6 +220,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
 #endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
+    if (const char* ev = getenv("AYQ_HOST_PASS")) e->host_pass = atoi(ev);
+    if (const char* ev = getenv("AYQ_HOST_RAMP")) e->host_ramp = atoi(ev);
     if (e->role_prof) {
         e->use_graph = false;
         cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
@@ -664,16 +667,32 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     CK(cudaSetDevice(e->device));
     // pass size of the host pipeline: H2D of pass i+1 overlaps the kernels of pass i, so the first copy and the last pass are
     // exposed -- smaller passes shorten both (64 images keep the kernels within ~10 % of their large-batch throughput)
-    const int mb = e->max_batch < 64 ? e->max_batch : 64;
+    const int host_pass = e->host_pass > 0 ? e->host_pass : 64;
+    const int mb = e->max_batch < host_pass ? e->max_batch : host_pass;
     const int m_max = n < mb ? n : mb;
+    // AYQ_HOST_RAMP=1 makes the passes at both ends smaller still (16, 32, ..., 32, 16).  Measured on B200 / PCIe 5 (256 uint8
+    // images per call): uniform 64-image passes 35.7 k images/s, ramp 31.8 k, uniform 32 28.9 k, uniform 128 28.4 k -- a pass
+    // has a fixed cost of ~0.5 ms (67 launches), so small passes fall behind the copy engine; the ramp stays off by default.
+    std::vector<int> sizes;
+    if (n <= mb || e->host_ramp == 0) {
+        for (int rem = n; rem > 0; rem -= mb) sizes.push_back(rem < mb ? rem : mb);
+    } else {
+        int rem = n;
+        std::vector<int> tail;
+        for (int t : {16, 32}) if (t < mb && rem - t >= mb) { tail.push_back(t); rem -= t; }
+        for (int h : {16, 32}) if (h < mb && rem - h >= mb / 2) { sizes.push_back(h); rem -= h; }
+        for (; rem > 0; rem -= mb) sizes.push_back(rem < mb ? rem : mb);
+        for (auto it = tail.rbegin(); it != tail.rend(); ++it) sizes.push_back(*it);
+    }
     int rc = ensure_workspace(e, n < e->max_batch ? n : e->max_batch);
     if (rc) return rc;
     rc = ensure_host_pipeline(e, m_max, u8);
     if (rc) return rc;
     const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
     int slot = 0, pass = 0;
-    for (int i0 = 0; i0 < n; i0 += mb, ++pass, slot ^= 1) {
-        const int m = (n - i0) < mb ? (n - i0) : mb;
+    int i0 = 0;
+    for (size_t pi = 0; pi < sizes.size(); i0 += sizes[pi], ++pi, ++pass, slot ^= 1) {
+        const int m = sizes[pi];
         // three streams: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i
         if (pass >= 2) CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));   // d_img[slot] still being read
         if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
