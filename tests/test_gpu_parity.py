@@ -312,3 +312,28 @@ def test_production_plan_intermediate_tensors_match_oracle(golden_dir):
             checked += 1
     assert checked >= 60, checked
     e.close()
+
+
+def test_full_size_batch_matches_oracle_and_is_copy_invariant(golden_dir):
+    """BASELINE configs[2] size: 256 images in ONE pass (plus a ragged 257th -> second pass).  The batch holds shuffled copies of
+    four distinct images: every copy must give the identical detections (no cross-image state at full occupancy of the
+    persistent kernels), and those must equal the oracle's for that image."""
+    p, e = _setup(golden_dir, 8, taps=False, impl='tma', max_batch=256)
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = Y.OracleYolov8(wl)
+    seeds = [1, 4, 7, 300]
+    base = _images(seeds)
+    ref = o.forward(base.numpy())
+    rng = np.random.default_rng(0)
+    which = rng.integers(0, len(seeds), 257)
+    which[:4] = [0, 1, 2, 3]
+    x = base[torch.from_numpy(which)].contiguous().cuda()
+    dets, counts = e.forward(x)
+    dets, counts = dets.cpu().numpy(), counts.cpu().numpy()
+    for i, w in enumerate(which):
+        b, c = ref[w]
+        k = int(counts[i])
+        assert k == (0 if b is None else b.shape[0]), (i, w, k)
+        if k:
+            assert np.array_equal(dets[i, :k, :4], b) and np.array_equal(dets[i, :k, 4:6], c), (i, w)
+    e.close()
