@@ -74,6 +74,7 @@ struct ayq_engine {
     std::map<int, cudaGraphExec_t> graphs; // per pass size: captured conv / pool / head section
     bool use_graph = true;
     int fast_div = 0;                      // DFL division shortcut verified on this device (div_selfcheck_kernel)
+    std::vector<int> host_tail;            // AYQ_HOST_TAIL=a,b,..: sizes the last pass of a host call is split into (sum = pass size)
     int host_pass = 0, host_ramp = 0;      // AYQ_HOST_PASS: pass size of the host pipeline (default 64); AYQ_HOST_RAMP=1: smaller passes at both ends
     int p1_chunk = 0;                      // AYQ_P1_CHUNK: images per abs-max -> Conv_P1 chunk (fp32 device input), 0 = whole pass
     bool p1_dp4a = false;                  // AYQ_P1_DP4A=1: keep Conv_P1 on the CUDA cores (conv_p1_fast_kernel) also when a tcgen05 conv family is selected
@@ -222,6 +223,9 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_PASS")) e->host_pass = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_RAMP")) e->host_ramp = atoi(ev);
+    if (const char* ev = getenv("AYQ_HOST_TAIL")) {
+        for (const char* q = ev; *q;) { e->host_tail.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    }
     if (e->role_prof) {
         e->use_graph = false;
         cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
@@ -673,9 +677,17 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     // AYQ_HOST_RAMP=1 makes the passes at both ends smaller still (16, 32, ..., 32, 16).  Measured on B200 / PCIe 5 (256 uint8
     // images per call): uniform 64-image passes 35.7 k images/s, ramp 31.8 k, uniform 32 28.9 k, uniform 128 28.4 k -- a pass
     // has a fixed cost of ~0.5 ms (67 launches), so small passes fall behind the copy engine; the ramp stays off by default.
+    // Splitting only the last pass (AYQ_HOST_TAIL) measured 33.5 k (32,32) / 33.3 k (48,16) / 31.4 k (32,16,16): also off.
     std::vector<int> sizes;
     if (n <= mb || e->host_ramp == 0) {
-        for (int rem = n; rem > 0; rem -= mb) sizes.push_back(rem < mb ? rem : mb);
+        // uniform passes; the LAST full pass may be split (AYQ_HOST_TAIL="32,32"): only the final pass's kernels are exposed
+        // after the last byte has arrived, so a smaller final pass ends the call sooner
+        int rem = n;
+        int tail_sum = 0;
+        for (int t : e->host_tail) tail_sum += t;
+        const bool split = !e->host_tail.empty() && n > mb && tail_sum <= mb && n % mb == 0 && tail_sum == mb;
+        for (; rem > (split ? mb : 0); rem -= mb) sizes.push_back(rem < mb ? rem : mb);
+        if (split) for (int t : e->host_tail) sizes.push_back(t);
     } else {
         int rem = n;
         std::vector<int> tail;
