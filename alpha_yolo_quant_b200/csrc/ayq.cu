@@ -808,6 +808,39 @@ extern "C" int ayq_quant_input_f32(const float* x, float* y, float* amax, float*
     CK(cudaGetLastError());
     return 0;
 }
+extern "C" int ayq_calib_conv_f32(const float* x, const float* w, const float* b, float* y, float* amax, int n, int cin, int H, int W,
+                                  int cout, int ks, int stride, void* stream) {
+    if (!x || !w || !b || !y || n < 0 || cin < 1 || cout < 1 || H < 1 || W < 1 || (ks != 1 && ks != 3) || (stride != 1 && stride != 2))
+        return fail(-22, "ayq_calib_conv_f32: bad arguments (kernel 1 or 3, stride 1 or 2)");
+    if (!n) return 0;
+    const int pad = ks / 2, Hout = (H + 2 * pad - ks) / stride + 1, Wout = (W + 2 * pad - ks) / stride + 1;
+    if (n > 65535 || (cout + CALIB_CO - 1) / CALIB_CO > 65535) return fail(-22, "ayq_calib_conv_f32: batch / channel count too large");
+    calib_conv_f32_kernel<<<dim3((unsigned)((Hout * Wout + 127) / 128), (unsigned)((cout + CALIB_CO - 1) / CALIB_CO), (unsigned)n), 128, 0, (cudaStream_t)stream>>>(
+        x, w, b, y, amax, cin, H, W, cout, Hout, Wout, ks, stride);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_calib_silu_f32(float* x, size_t count, void* stream) {
+    if (!x) return fail(-22, "ayq_calib_silu_f32: null pointer");
+    if (!count) return 0;
+    calib_silu_f32_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_calib_maxpool5_f32(const float* x, float* y, int planes, int H, int W, void* stream) {
+    if (!x || !y || planes < 0 || H < 1 || W < 1) return fail(-22, "ayq_calib_maxpool5_f32: bad arguments");
+    if (!planes) return 0;
+    calib_maxpool5_f32_kernel<<<grid_for((size_t)planes * H * W), 256, 0, (cudaStream_t)stream>>>(x, y, planes, H, W);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ayq_calib_upsample2_f32(const float* x, float* y, int planes, int H, int W, void* stream) {
+    if (!x || !y || planes < 0 || H < 1 || W < 1) return fail(-22, "ayq_calib_upsample2_f32: bad arguments");
+    if (!planes) return 0;
+    calib_upsample2_f32_kernel<<<grid_for((size_t)planes * H * W * 4), 256, 0, (cudaStream_t)stream>>>(x, y, planes, H, W);
+    CK(cudaGetLastError());
+    return 0;
+}
 extern "C" int ayq_quant_weights_f32(const float* w, const float* bias, int cout, size_t per_channel, int bits, double scale_input,
                                      int8_t* qw, int64_t* qb, double* scale_res, void* stream) {
     if (!w || !bias || !qw || !qb || !scale_res || cout < 0 || bits < 2 || bits > 8) return fail(-22, "ayq_quant_weights_f32: bad arguments (bits 2..8)");

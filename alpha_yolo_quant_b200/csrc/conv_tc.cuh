@@ -200,38 +200,45 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
     unsigned carry = 0u;
     uint32_t phase = 0;
     const int e = (tid >> 7) & 1, row = tid & 127, ty = row >> 4, h = row & 15;
-    // one CTA walks the whole band of x tiles: tables, weights, TMEM allocation and barrier are set up once per band
-    for (int x0 = 0; x0 < a.Wout; x0 += P1_TW) {
-        if (loader) {
-            unsigned w0 = 0u, w1 = 0u, w2 = 0u;
-            if (lvalid) {
-                unsigned q[3][4];                                  // [channel][pixel], value in byte 0
-                if (U8) {
+    // quantise the prefetched 4 pixels x 3 channels into the byte-interleaved patch row (and the carried halo pixel)
+    auto stage_patch = [&]() {
+        if (!loader) return;
+        unsigned w0 = 0u, w1 = 0u, w2 = 0u;
+        if (lvalid) {
+            unsigned q[3][4];                                      // [channel][pixel], value in byte 0
+            if (U8) {
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        q[0][p] = qlut[(pu0 >> (8 * p)) & 0xffu]; q[1][p] = qlut[(pu1 >> (8 * p)) & 0xffu]; q[2][p] = qlut[(pu2 >> (8 * p)) & 0xffu];
-                    }
-                } else {
-                    const float f[3][4] = {{pf0.x, pf0.y, pf0.z, pf0.w}, {pf1.x, pf1.y, pf1.z, pf1.w}, {pf2.x, pf2.y, pf2.z, pf2.w}};
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) q[c][p] = __float_as_uint(__fadd_rn(__fmul_rn(f[c][p], s), AYQ_MAGIC_F));
+                for (int p = 0; p < 4; ++p) {
+                    q[0][p] = qlut[(pu0 >> (8 * p)) & 0xffu]; q[1][p] = qlut[(pu1 >> (8 * p)) & 0xffu]; q[2][p] = qlut[(pu2 >> (8 * p)) & 0xffu];
                 }
-                // 12 bytes, channel fastest: (p0c0 p0c1 p0c2 p1c0) (p1c1 p1c2 p2c0 p2c1) (p2c2 p3c0 p3c1 p3c2)
-                w0 = __byte_perm(__byte_perm(q[0][0], q[1][0], 0x0040), __byte_perm(q[2][0], q[0][1], 0x0040), 0x5410);
-                w1 = __byte_perm(__byte_perm(q[1][1], q[2][1], 0x0040), __byte_perm(q[0][2], q[1][2], 0x0040), 0x5410);
-                w2 = __byte_perm(__byte_perm(q[2][2], q[0][3], 0x0040), __byte_perm(q[1][3], q[2][3], 0x0040), 0x5410);
+            } else {
+                const float f[3][4] = {{pf0.x, pf0.y, pf0.z, pf0.w}, {pf1.x, pf1.y, pf1.z, pf1.w}, {pf2.x, pf2.y, pf2.z, pf2.w}};
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) q[c][p] = __float_as_uint(__fadd_rn(__fmul_rn(f[c][p], s), AYQ_MAGIC_F));
             }
-            sQ[lr][1 + 3 * lg] = w0; sQ[lr][2 + 3 * lg] = w1; sQ[lr][3 + 3 * lg] = w2;
-            if (lg == GROUPS - 1) { sQ[lr][0] = carry; carry = w2 & 0xffffff00u; }    // halo pixel -> bytes 1..3 of word 0
+            // 12 bytes, channel fastest: (p0c0 p0c1 p0c2 p1c0) (p1c1 p1c2 p2c0 p2c1) (p2c2 p3c0 p3c1 p3c2)
+            w0 = __byte_perm(__byte_perm(q[0][0], q[1][0], 0x0040), __byte_perm(q[2][0], q[0][1], 0x0040), 0x5410);
+            w1 = __byte_perm(__byte_perm(q[1][1], q[2][1], 0x0040), __byte_perm(q[0][2], q[1][2], 0x0040), 0x5410);
+            w2 = __byte_perm(__byte_perm(q[2][2], q[0][3], 0x0040), __byte_perm(q[1][3], q[2][3], 0x0040), 0x5410);
         }
-        __syncthreads();
-        if (lvalid && x0 + P1_TW < a.Wout) {                      // next tile's pixels: in flight during the rest of this iteration
-            const size_t o = lbase + 2 * (x0 + P1_TW);
-            if (U8) { pu0 = __ldg((const unsigned*)(a.img_u8 + o)); pu1 = __ldg((const unsigned*)(a.img_u8 + o + cs)); pu2 = __ldg((const unsigned*)(a.img_u8 + o + 2 * cs)); }
-            else { pf0 = __ldg((const float4*)(a.img + o)); pf1 = __ldg((const float4*)(a.img + o + cs)); pf2 = __ldg((const float4*)(a.img + o + 2 * cs)); }
-        }
+        sQ[lr][1 + 3 * lg] = w0; sQ[lr][2 + 3 * lg] = w1; sQ[lr][3 + 3 * lg] = w2;
+        if (lg == GROUPS - 1) { sQ[lr][0] = carry; carry = w2 & 0xffffff00u; }        // halo pixel -> bytes 1..3 of word 0
+    };
+    auto fetch_patch = [&](int x0n) {                              // pixels of the tile at x0n into the prefetch registers
+        if (!lvalid || x0n >= a.Wout) return;
+        const size_t o = lbase + 2 * x0n;
+        if (U8) { pu0 = __ldg((const unsigned*)(a.img_u8 + o)); pu1 = __ldg((const unsigned*)(a.img_u8 + o + cs)); pu2 = __ldg((const unsigned*)(a.img_u8 + o + 2 * cs)); }
+        else { pf0 = __ldg((const float4*)(a.img + o)); pf1 = __ldg((const float4*)(a.img + o + cs)); pf2 = __ldg((const float4*)(a.img + o + 2 * cs)); }
+    };
+    // One CTA walks the whole band of x tiles: tables, weights, TMEM allocation and barrier are set up once per band.  Software
+    // pipeline: while the tensor core multiplies tile i (asynchronously), the threads quantise tile i+1 into the patch buffer
+    // (free again once the im2col copy of tile i is done) and fetch tile i+2 into registers; then they post-process tile i.
+    stage_patch();                                                 // tile 0 (fetched above)
+    fetch_patch(P1_TW);
+    __syncthreads();
+    for (int x0 = 0; x0 < a.Wout; x0 += P1_TW) {
         if (warp < 8) {                                           // im2col: three aligned words per filter row
             const int wi = 3 * h + e;
 #pragma unroll
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                                          // A tiles complete; the patch buffer is free
         if (tid == 0) {
             tc_fence_after();
             const uint32_t idesc = make_idesc_i8(16);
@@ -256,6 +263,10 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
             mma_commit(smem_u32(&bar));
         }
         __syncwarp();
+        if (x0 + P1_TW < a.Wout) {
+            stage_patch();                                        // tile i+1 -> patch buffer (overlaps the MMA)
+            fetch_patch(x0 + 2 * P1_TW);                          // tile i+2 -> registers
+        }
         if (warp < 8) {
             mbar_wait(smem_u32(&bar), phase);
             tc_fence_after();
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
         }
         phase ^= 1u;
         tc_fence_before();
-        __syncthreads();                                          // accumulators read, patch consumed: the next tile may overwrite both
+        __syncthreads();                                          // accumulators read, next patch staged: the next tile may proceed
         tc_fence_after();
     }
     if (warp == 0) {

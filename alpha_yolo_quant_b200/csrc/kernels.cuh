@@ -1149,6 +1149,92 @@ __global__ void __launch_bounds__(256) quant_weights_kernel(const float* __restr
         qw[(size_t)c * per_channel + i] = isfinite(s) ? (int8_t)__float2int_rn(__fmul_rn(wc[i], s)) : (int8_t)0;
 }
 
+// ---- calibration forward (stage_4.py:475-946): the BN-fused FLOAT network with abs-max taps -------
+// Not a hot path (a handful of calibration images per bit-width sweep); plain fp32 kernels, NCHW like the reference.
+// conv: grid (ceil(Hout*Wout / 128), ceil(cout / 16), n), block 128: one output pixel x 16 output channels per thread, weights of
+// 8 input channels at a time in shared memory, FMA accumulation; the per-image abs-max tap (save_max_a, utils/save_a.py:22) is
+// fused: amax[img] = max(amax[img], max|y|) through an integer atomicMax on the (non-negative) float bits.
+#define CALIB_CO 16
+#define CALIB_CI 8
+__global__ void __launch_bounds__(128) calib_conv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                             float* __restrict__ y, float* __restrict__ amax, int cin, int H, int W,
+                                                             int cout, int Hout, int Wout, int ks, int stride) {
+    __shared__ float sw[CALIB_CI * 9 * CALIB_CO];                 // [ci][tap][co]
+    const int pad = ks >> 1, taps = ks * ks;
+    const int img = blockIdx.z, co0 = blockIdx.y * CALIB_CO;
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    const bool live = p < Hout * Wout;
+    const int oy = live ? p / Wout : 0, ox = live ? p - oy * Wout : 0;
+    float acc[CALIB_CO];
+#pragma unroll
+    for (int j = 0; j < CALIB_CO; ++j) acc[j] = co0 + j < cout ? __ldg(b + co0 + j) : 0.f;
+    const float* xi = x + (size_t)img * cin * H * W;
+    for (int c0 = 0; c0 < cin; c0 += CALIB_CI) {
+        const int nc = min(CALIB_CI, cin - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * taps * CALIB_CO; i += 128) {
+            const int j = i % CALIB_CO, t = (i / CALIB_CO) % taps, c = i / (CALIB_CO * taps);
+            sw[i] = co0 + j < cout ? __ldg(w + ((size_t)(co0 + j) * cin + c0 + c) * taps + t) : 0.f;
+        }
+        __syncthreads();
+        if (live) {
+            for (int c = 0; c < nc; ++c) {
+                const float* xc = xi + (size_t)(c0 + c) * H * W;
+                for (int t = 0; t < taps; ++t) {
+                    const int iy = oy * stride + t / ks - pad, ix = ox * stride + t % ks - pad;
+                    if ((unsigned)iy >= (unsigned)H || (unsigned)ix >= (unsigned)W) continue;
+                    const float v = __ldg(xc + (size_t)iy * W + ix);
+                    const float* wr = sw + (c * taps + t) * CALIB_CO;
+#pragma unroll
+                    for (int j = 0; j < CALIB_CO; ++j) acc[j] = __fmaf_rn(v, wr[j], acc[j]);
+                }
+            }
+        }
+    }
+    float m = 0.f;
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < CALIB_CO; ++j)
+            if (co0 + j < cout) {
+                y[(((size_t)img * cout + co0 + j) * Hout + oy) * Wout + ox] = acc[j];
+                m = fmaxf(m, fabsf(acc[j]));
+            }
+    }
+    if (amax) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax((int*)amax + img, __float_as_int(m));
+    }
+}
+__global__ void calib_silu_f32_kernel(float* __restrict__ x, size_t total) {                    // nn.SiLU: x * sigmoid(x)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        x[i] = __fdiv_rn(v, 1.f + expf(-v));
+    }
+}
+__global__ void calib_maxpool5_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W) {   // MaxPool2d(5, 1, 2)
+    const size_t total = (size_t)planes * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W), yy = (int)((i / W) % H);
+        const float* pl = x + (i / ((size_t)H * W)) * H * W;
+        float m = -INFINITY;
+        for (int dy = -2; dy <= 2; ++dy)
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int iy = yy + dy, ix = xx + dx;
+                if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) m = fmaxf(m, pl[(size_t)iy * W + ix]);
+            }
+        y[i] = m;
+    }
+}
+__global__ void calib_upsample2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W) { // nearest, x2
+    const size_t total = (size_t)planes * H * W * 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % (2 * W)), yy = (int)((i / (2 * W)) % (2 * H));
+        const size_t pl = i / ((size_t)4 * H * W);
+        y[i] = x[pl * H * W + (size_t)(yy >> 1) * W + (xx >> 1)];
+    }
+}
+
 // ---- export a plane buffer as NCHW int32 (parity taps) ------------------------------------------------
 __global__ void export_planes_kernel(const void* __restrict__ src, int elem_bytes, int nplanes, int n, int H, int W, int* __restrict__ dst) {
     const size_t total = (size_t)n * nplanes * 16 * H * W;

@@ -43,6 +43,10 @@ SIGNATURES = {
     'ayq_nms': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'ayq_nms_boxes': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
     'ayq_coord_float': (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    'ayq_calib_conv_f32': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
+    'ayq_calib_silu_f32': (_int, [_vp, _sz, _vp]),
+    'ayq_calib_maxpool5_f32': (_int, [_vp, _vp, _int, _int, _int, _vp]),
+    'ayq_calib_upsample2_f32': (_int, [_vp, _vp, _int, _int, _int, _vp]),
     'ayq_quant_weights_f32': (_int, [_vp, _vp, _int, _sz, _int, _c.c_double, _vp, _vp, _vp, _vp]),
 }
 

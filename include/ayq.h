@@ -90,6 +90,17 @@ int ayq_lut_f32(const float* x, float* y, const float* lut, int key_min, int key
 int ayq_quant_input_f32(const float* x, float* y, float* amax, float* scales, int n, size_t per_image, int bits, void* stream);
 /* save_max_a(), utils/save_a.py:11-26: out[i] = max|x[i, :]| over per_image floats (calibration taps). */
 int ayq_absmax_f32(const float* x, float* out, int n, size_t per_image, void* stream);
+/* Calibration forward (stage_4.py:475-946): the BN-fused float network, NCHW float32 like the reference.
+ * ayq_calib_conv_f32: y = Conv2d(x; w, b, kernel ks in {1,3}, stride in {1,2}, padding ks/2); when amax != NULL the tap of
+ * save_max_a() (utils/save_a.py:22) is fused: amax[i] = max(amax[i], max|y[i]|) per image (the caller zeroes amax).
+ * x (n,cin,H,W), w (cout,cin,ks,ks), b (cout), y (n,cout,Hout,Wout), amax (n): device float32.
+ * ayq_calib_silu_f32: nn.SiLU in place.  ayq_calib_maxpool5_f32: MaxPool2d(5,1,2) on `planes` = n*c planes of H x W.
+ * ayq_calib_upsample2_f32: nn.Upsample(None, 2, 'nearest'), y has planes x 2H x 2W elements. */
+int ayq_calib_conv_f32(const float* x, const float* w, const float* b, float* y, float* amax, int n, int cin, int H, int W,
+                       int cout, int ks, int stride, void* stream);
+int ayq_calib_silu_f32(float* x, size_t count, void* stream);
+int ayq_calib_maxpool5_f32(const float* x, float* y, int planes, int H, int W, void* stream);
+int ayq_calib_upsample2_f32(const float* x, float* y, int planes, int H, int W, void* stream);
 /* conv_quant() of stage_6_full_quant.py:89-126 without its text dumps (the producer of the stage_7 weights):
  * per output channel a = max|w|, s = fl32((2^(bits-1)-1) / a), qw = rint(fl32(w * s)) (utils/quant_matrix.py:56-78);
  * qb = trunc(double(bias) * (scale_input * s)) (utils/quant_bias.py:2-4); scale_res = scale_input * s (:93-96,:122; the first

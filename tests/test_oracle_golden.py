@@ -146,3 +146,20 @@ def test_weight_quant_oracle_matches_reference(golden_dir):
         assert np.array_equal(q, g[f'{l}/qw'].astype(np.int64)), l
         assert np.array_equal(b, g[f'{l}/qb']), l
         assert np.array_equal(s, g[f'{l}/scale_res']), l
+
+
+# ---- calibration forward, oracle/calib_float.py --------------------------------------------------
+def test_calibration_oracle_matches_reference_taps(golden_dir):
+    """The reference's own results/max_a_all.txt (six calibration images) for every tap up to Conv_P3, from the committed
+    125 KB weights fixture; tools/pin_calib_oracle.py checks all 64 taps where the full 12 MB fused weights exist."""
+    from oracle import calib_float as C
+    g = np.load(os.path.join(golden_dir, 'bnf_head_k8.npz'))
+    ref = C.parse_max_a_all(str(g['max_a_all_txt']))
+    assert len(ref) == 64
+    sd = {k: g[k] for k in g.files if k.endswith('.weight') or k.endswith('.bias')}
+    o = C.CalibOracle(sd, stop_after='Conv_P3')
+    for i in range(synth.N_CALIB):
+        taps = o.forward(synth.to_input_array([synth.synth_image_u8(1000 + i)]))
+        assert [n for n, _ in taps] == [n for n, _ in ref[:8]]
+        for (n, v), (_, vals) in zip(taps, ref[:8]):
+            assert abs(round(v, 4) - vals[i]) <= 1.01e-4, (n, i, v, vals[i])
