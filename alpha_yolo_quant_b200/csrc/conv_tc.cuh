@@ -361,10 +361,25 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
 // (c0 compile-time) or from shared memory.  acc[] = raw accumulators (bias not yet added).
 // FAST: the common case -- K = 8 (clamp 127), one identity output, no accumulator tap: straight-line code, FOLDED
 // coefficients (k1 / k2 hold k * 2^-s, see fixedpoint.cuh; i1 / i2 unused) and 32-bit store offsets.
+// Store offsets of one output pixel, computed ONCE per tile by the caller of the FAST epilogues (32-bit, bytes): the 16-byte row of
+// channel group g lives at pix16 + g * plane16 (plane layout) and at ps_pix16 + g * ps_plane16 (phase-split layout).
+struct StoreOff { uint32_t pix16, plane16, ps_pix16, ps_plane16; };
+__device__ __forceinline__ StoreOff store_off(const ConvArgs& a, int img, int oy, int ox) {
+    StoreOff so;
+    const uint32_t npix = (uint32_t)a.n * (uint32_t)a.Hout * (uint32_t)a.Wout;
+    so.plane16 = npix * 16u;
+    so.pix16 = (((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox) * 16u;
+    const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
+    so.ps_plane16 = (uint32_t)a.n * H2 * W2 * 16u;
+    const uint32_t ph = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)a.cout >> 4);
+    so.ps_pix16 = (((ph * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u;
+    return so;
+}
+
 template <int EPI, bool CT, int FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
-                                             const float* __restrict__ lut_s) {
+                                             const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u}) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
     int r[16];
@@ -383,10 +398,10 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             else r[4 * q + j] = FAST ? requant16_f(__int2float_rn(v), cf.k1[j], half) : requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
         }
     }
-    if (FAST) {                       // every output buffer is < 4 GB (checked by the host): 32-bit offsets
-        const uint32_t npix = (uint32_t)a.n * (uint32_t)a.Hout * (uint32_t)a.Wout;
-        const uint32_t pix = ((uint32_t)img * (uint32_t)a.Hout + (uint32_t)oy) * (uint32_t)a.Wout + (uint32_t)ox;
-        const uint32_t off = ((uint32_t)(c0 >> 4) * npix + pix) * 16u;
+    if (FAST) {                       // every output buffer is < 4 GB (checked by the host): 32-bit offsets, per-tile part in `so`
+        const uint32_t npix = so.plane16 >> 4;
+        const uint32_t off = (uint32_t)(c0 >> 4) * so.plane16 + so.pix16;
+        const uint32_t ps_off = (uint32_t)(c0 >> 4) * so.ps_plane16 + so.ps_pix16;
         if (EPI == 0 && FAST == 2 && a.gen_outs) {
             // general output list.  A requantised copy (requantize(silu, old, new) with SCALAR coefficients, e.g. :741, :903) is
             // a function of the 8-bit SiLU result alone: one byte load from the 256-entry table the prologue built with the
@@ -408,9 +423,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
                 if (os.up == 0) {
                     *(uint4*)(base + off) = v;
                 } else if (os.up == 2) {
-                    const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
-                    const uint32_t plane = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)N >> 4) + (uint32_t)(c0 >> 4);
-                    *(uint4*)(base + (((plane * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u) = v;
+                    *(uint4*)(base + ps_off) = v;
                 } else {                 // 2x nearest upsample (:900, :935): 2x2 replicate
                     const uint32_t W2 = (uint32_t)a.Wout * 2u;
                     const uint32_t p00 = ((uint32_t)img * (uint32_t)a.Hout * 2u + 2u * (uint32_t)oy) * W2 + 2u * (uint32_t)ox;
@@ -427,10 +440,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             const uint4 v = FAST == 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
                                       : make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
             if (EPI == 0 && a.out[a.nout - 1].up == 2) {           // phase-split copy (alone, or next to the plain tensor)
-                const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
-                const uint32_t plane = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)N >> 4) + (uint32_t)(c0 >> 4);
-                const uint32_t poff = (((plane * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u;
-                *(uint4*)((int8_t*)a.out[a.nout - 1].base + poff) = v;
+                *(uint4*)((int8_t*)a.out[a.nout - 1].base + ps_off) = v;
                 if (a.nout == 1) return;
             }
             *(uint4*)((int8_t*)a.out[0].base + off) = v;

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
+            const StoreOff so = FAST ? store_off(a, img, oy, ox) : StoreOff{0u, 0u, 0u, 0u};   // per-tile part of the store addresses
             const long long w0 = AYQ_CLK(a);
             mbar_wait(tfull_b, (tphase >> buf) & 1u);
             tphase ^= 1u << buf;
@@ -297,18 +298,18 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     tmem_ld_wait16(cur);
                     if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
                     else { tc_fence_before(); mbar_arrive(tempty_b); }   // accumulator fully read: hand it back to the MMA warp
-                    if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
                 }
             } else {
                 const int nb = N / 16;                                   // even, checked by the host
                 for (int gch = 0; gch < nb; gch += 2) {
                     tmem_ld_wait16(accA);
                     tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
-                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
                     tmem_ld_wait16(accB);
                     if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
                     else { tc_fence_before(); mbar_arrive(tempty_b); }
-                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
                 }
             }
             if (EG == 1 && nbuf == 2) buf ^= 1;
