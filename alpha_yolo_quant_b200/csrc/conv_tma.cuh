@@ -80,13 +80,18 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 // dynamic smem: [A ring NS*slot_chunks*2048][B: resident nkc_pad*N*16 | ring NS*slot_chunks*N*16][tab 4N f32][bias N i32][lut 256 f32]
 // EG = epilogue groups per pipeline: 2 (one group per TMEM buffer) for cout <= 32, where the epilogue is the issue-bound
 // stage and the kernels are small enough in registers for 768 threads; 1 otherwise (the group alternates buffers).
-template <int NBC, int EPI, int FAST, int EG = (NBC > 0 ? 2 : 1)>
+// EG = epilogue groups (of 4 warps) per pipeline = TMEM accumulator buffers per pipeline when EG >= 2 (group k owns buffer k and
+// every EG-th tile of its pipeline).  3 for cout <= 32 (1024 threads at <= 64 registers: these layers are bound by instruction
+// issue in the epilogue, more resident epilogue warps hide its latencies), 2 for the other compile-time-cout kernels, 1 otherwise.
+#define TMA_EG(NBC) ((NBC) == 1 || (NBC) == 2 ? 3 : ((NBC) > 0 ? 2 : 1))
+constexpr int TMA_NB = 3;                                          // barrier slots per pipeline for the accumulator buffers
+template <int NBC, int EPI, int FAST, int EG = TMA_EG(NBC)>
 __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
     constexpr int TMA_THREADS = 256 + 256 * EG;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 9];   // full[NS], empty[NS], tfull[4], tempty[4], wfull
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 2 * 2 * TMA_NB + 1];   // full[NS], empty[NS], tfull[2][NB], tempty[2][NB], wfull
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.cout, NS = tp.NS;
@@ -98,8 +103,8 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     int* bias_s = (int*)(tab_s + 4 * N);
     float* lut_s = (float*)(bias_s + N);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 4]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 8]);
-    const int nbuf = tp.tmem_cols >= 4 * N ? 2 : 1;               // TMEM accumulator buffers per pipeline (cout 256: one)
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2 * TMA_NB]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4 * TMA_NB]);
+    const int nbuf = EG >= 2 ? EG : (tp.tmem_cols >= 4 * N ? 2 : 1);   // TMEM accumulator buffers per pipeline (cout 256: one)
 
     pdl_trigger();
     // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     else if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        for (int b = 0; b < 2 * TMA_NB; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
         if (!tp.resident_b) mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -218,11 +223,11 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         const TmaStage sg0 = pl.st[0];
         const int slot0 = m * NSH;
         int slot = 0, buf = 0;
-        uint32_t fphase = 0, ephase = 3;                           // bit buf = parity to wait for on tempty[m][buf]; fresh barriers pass parity 1
+        uint32_t fphase = 0, ephase = 7;                           // bit buf = parity to wait for on tempty[m][buf]; fresh barriers pass parity 1
         long long d_we = 0, d_wf = 0, d_t0 = AYQ_CLK(a);
         for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
             const long long w0 = AYQ_CLK(a);
-            mbar_wait(tempty0 + 8 * (2 * m + buf), (ephase >> buf) & 1u);
+            mbar_wait(tempty0 + 8 * (TMA_NB * m + buf), (ephase >> buf) & 1u);
             if (AYQ_DBG(a)) d_we += clock64() - w0;
             ephase ^= 1u << buf;
             tc_fence_after();
@@ -256,29 +261,29 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                         }
                     }
                     mma_commit(empty0 + 8 * gs);                  // frees the smem slot when these MMAs retire
-                    if (s == nstages - 1) mma_commit(tfull0 + 8 * (2 * m + buf));   // accumulator complete -> epilogue group m
+                    if (s == nstages - 1) mma_commit(tfull0 + 8 * (TMA_NB * m + buf));   // accumulator complete -> epilogue group m
                 }
                 __syncwarp();
                 accum = 1;
                 if (++slot == NSH) { slot = 0; fphase ^= 1; }
             }
-            if (nbuf == 2) buf ^= 1;
+            if (++buf == nbuf) buf = 0;
         }
         if (AYQ_DBG(a) && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int gq = (warp - 8) >> 2;
-        const int grp = EG == 2 ? (gq >> 1) : gq;                // pipeline (tile parity) this group drains
-        const int tstep = EG == 2 ? 4 : 2;                       // EG == 2: group (grp, gq & 1) owns TMEM buffer gq & 1, every other tile of the pipeline
+        const int grp = gq / EG, gk = gq - grp * EG;              // pipeline (tile parity) this group drains; its index inside the pipeline
+        const int tstep = 2 * EG;                                // EG >= 2: group (grp, gk) owns TMEM buffer gk and every EG-th tile of the pipeline
         const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
         const uint32_t lane_quad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tphase = 0;                                     // bit buf = parity to wait for on tfull[grp][buf]
-        int buf = EG == 2 ? (gq & 1) : 0;
+        int buf = EG >= 2 ? gk : 0;
         long long d_wt = 0, d_t0 = AYQ_CLK(a);
-        for (int t = blockIdx.x + (grp + 2 * (EG == 2 ? (gq & 1) : 0)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
+        for (int t = blockIdx.x + (grp + 2 * gk) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
-            const uint32_t tfull_b = tfull0 + 8 * (2 * grp + buf), tempty_b = tempty0 + 8 * (2 * grp + buf);
+            const uint32_t tfull_b = tfull0 + 8 * (TMA_NB * grp + buf), tempty_b = tempty0 + 8 * (TMA_NB * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             }
             if (EG == 1 && nbuf == 2) buf ^= 1;
         }
-        if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gq < 2) { a.dbg[blockIdx.x * 16 + 12 + 2 * gq] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * gq] = d_wt; }
+        if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gk == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
     }
     tc_fence_before();
     __syncthreads();
@@ -366,6 +371,11 @@ static inline TmaKernel tma_pick_t(int N, int epi) {
 }
 static inline TmaKernel tma_pick(int N, int epi, int fast) { return fast == 2 ? tma_pick_t<2>(N, epi) : fast ? tma_pick_t<1>(N, epi) : tma_pick_t<0>(N, epi); }
 // FAST epilogue: clamp 127 (16-bit logits: 32767), a single identity output, no accumulator tap
+// epilogue groups per pipeline of the kernel tma_pick() returns for this cout (must mirror TMA_EG / the switch in tma_pick_t)
+static inline int tma_eg(int N, int epi) {
+    if (epi == 0) return (N == 16 || N == 32) ? 3 : ((N == 64 || N == 80) ? 2 : 1);
+    return (epi == 1 && N == 64) || (epi == 2 && N == 80) ? 2 : 1;
+}
 static inline bool tma_fast(const ConvArgs& a) {
     if (a.acc_tap) return false;
     if ((unsigned long long)a.n * a.cout * a.Hout * a.Wout * (a.epi == 2 ? 2 : 1) >= (1ull << 32)) return false;   // 32-bit store offsets
@@ -473,7 +483,8 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
     tp.KS = slot_chunks; tp.nst = 0; tp.lag = 0;
     int cols = 32;
-    while (cols < (4 * N <= 512 ? 4 : 2) * N) cols <<= 1;        // two pipelines x two accumulator buffers (one for cout 256)
+    const int eg = tma_eg(N, a.epi);
+    while (cols < (eg >= 2 ? 2 * eg : (4 * N <= 512 ? 4 : 2)) * N) cols <<= 1;   // two pipelines x EG accumulator buffers (cout 128: two, 256: one)
     tp.tmem_cols = cols;
 
     tc::TmaPlan& pl = L.pl;
@@ -673,7 +684,7 @@ static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t
     TmaKernel kern = tma_pick(a.cout, a.epi, L.fast);
     ConvArgs a2 = a;
     a2.gen_outs = L.gen_outs;
-    return launch_k(kern, dim3(L.grid), dim3(a.cout <= TC_CT_MAXN ? 768 : 512), L.smem, st, a2, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
+    return launch_k(kern, dim3(L.grid), dim3(256 + 256 * tma_eg(a.cout, a.epi)), L.smem, st, a2, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace ayq
