@@ -54,6 +54,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (it > (1u << 27)) __trap();
     }
 }
+// Same, for waits that are far from the critical path (a producer waiting for a ring slot to drain): back off between probes so
+// that the polling does not compete with the epilogue warps for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t it = 0;; ++it) {
+        __nanosleep(96);
+        if (mbar_try_wait(bar, parity)) return;
+        if (it > (1u << 25)) __trap();
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -363,7 +373,7 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
 // coefficients (k1 / k2 hold k * 2^-s, see fixedpoint.cuh; i1 / i2 unused) and 32-bit store offsets.
 // Store offsets of one output pixel, computed ONCE per tile by the caller of the FAST epilogues (32-bit, bytes): the 16-byte row of
 // channel group g lives at pix16 + g * plane16 (plane layout) and at ps_pix16 + g * ps_plane16 (phase-split layout).
-struct StoreOff { uint32_t pix16, plane16, ps_pix16, ps_plane16; };
+struct StoreOff { uint32_t pix16, plane16, ps_pix16, ps_plane16; uint32_t mode; };   // mode: 0 plain tensor, 1 phase-split only, 2 both
 __device__ __forceinline__ StoreOff store_off(const ConvArgs& a, int img, int oy, int ox) {
     StoreOff so;
     const uint32_t npix = (uint32_t)a.n * (uint32_t)a.Hout * (uint32_t)a.Wout;
@@ -373,13 +383,14 @@ __device__ __forceinline__ StoreOff store_off(const ConvArgs& a, int img, int oy
     so.ps_plane16 = (uint32_t)a.n * H2 * W2 * 16u;
     const uint32_t ph = (uint32_t)(((oy & 1) << 1) | (ox & 1)) * ((uint32_t)a.cout >> 4);
     so.ps_pix16 = (((ph * (uint32_t)a.n + (uint32_t)img) * H2 + (uint32_t)(oy >> 1)) * W2 + (uint32_t)(ox >> 1)) * 16u;
+    so.mode = a.out[a.nout - 1].up == 2 ? (a.nout == 1 ? 1u : 2u) : 0u;
     return so;
 }
 
 template <int EPI, bool CT, int FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
-                                             const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u}) {
+                                             const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u, 0u}) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
     int r[16];
@@ -439,11 +450,8 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         if (EPI != 2) {
             const uint4 v = FAST == 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
                                       : make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
-            if (EPI == 0 && a.out[a.nout - 1].up == 2) {           // phase-split copy (alone, or next to the plain tensor)
-                *(uint4*)((int8_t*)a.out[a.nout - 1].base + ps_off) = v;
-                if (a.nout == 1) return;
-            }
-            *(uint4*)((int8_t*)a.out[0].base + off) = v;
+            if (EPI == 0 && so.mode != 0u) *(uint4*)((int8_t*)a.out[a.nout - 1].base + ps_off) = v;   // phase-split copy (alone, or next to the plain tensor)
+            if (EPI != 0 || so.mode != 1u) *(uint4*)((int8_t*)a.out[0].base + off) = v;
         } else {
             uint32_t wd[8];
 #pragma unroll

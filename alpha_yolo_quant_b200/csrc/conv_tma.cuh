@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     const TmaStage sg = pl.st[s];
                     const int gs = slot0 + slot;
                     const long long w0 = AYQ_CLK(a);
-                    mbar_wait(empty0 + 8 * gs, ephase);
+                    mbar_wait_relaxed(empty0 + 8 * gs, ephase);
                     if (AYQ_DBG(a)) d_wait += clock64() - w0;
                     if (elect_one()) {
                         const uint32_t bar = full0 + 8 * gs;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n;
-            const StoreOff so = FAST ? store_off(a, img, oy, ox) : StoreOff{0u, 0u, 0u, 0u};   // per-tile part of the store addresses
+            const StoreOff so = FAST ? store_off(a, img, oy, ox) : StoreOff{0u, 0u, 0u, 0u, 0u};   // per-tile part of the store addresses
             const long long w0 = AYQ_CLK(a);
             mbar_wait(tfull_b, (tphase >> buf) & 1u);
             tphase ^= 1u << buf;
