@@ -55,59 +55,47 @@ def silu(x, scale_x, a_input):
 
 
 def make_anchors(feats, strides, grid_cell_offset=0.5):
-    """:97-109 (torch plumbing on the caller's device; the engine's head kernel builds the same anchors itself)"""
-    anchor_points, stride_tensor = [], []
-    dtype, dev = feats[0].dtype, feats[0].device
-    for i, stride in enumerate(strides):
-        _, _, h, w = feats[i].shape
-        sx = torch.arange(end=w, device=dev, dtype=dtype) + grid_cell_offset
-        sy = torch.arange(end=h, device=dev, dtype=dtype) + grid_cell_offset
-        sy, sx = torch.meshgrid(sy, sx, indexing='ij')
-        anchor_points.append(torch.stack((sx, sy), -1).view(-1, 2))
-        stride_tensor.append(torch.full((h * w, 1), float(stride), dtype=dtype, device=dev))
-    return torch.cat(anchor_points).transpose(0, 1), torch.cat(stride_tensor).transpose(0, 1)
+    """:97-109: anchor centres (2, A) and their strides (1, A) for the given feature maps (torch plumbing on the caller's
+    device; the engine's head kernel derives the same anchors from the anchor index)."""
+    pts, strd = [], []
+    for f, st in zip(feats, strides):
+        h, w = f.shape[-2:]
+        ys = torch.arange(h, device=f.device, dtype=f.dtype) + grid_cell_offset
+        xs = torch.arange(w, device=f.device, dtype=f.dtype) + grid_cell_offset
+        pts.append(torch.stack((xs.repeat(h), ys.repeat_interleave(w)), 0))          # row-major: x fastest
+        strd.append(torch.full((1, h * w), float(st), device=f.device, dtype=f.dtype))
+    return torch.cat(pts, 1), torch.cat(strd, 1)
 
 
 def dist2bbox(distance, anchor_points, xywh=True, dim=-1):
-    """:112-121"""
-    lt, rb = distance.chunk(2, dim)
-    x1y1 = anchor_points - lt
-    x2y2 = anchor_points + rb
-    if xywh:
-        return torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), dim)
-    return torch.cat((x1y1, x2y2), dim)
+    """:112-121: (left, top, right, bottom) distances around the anchor -> xywh (default) or xyxy boxes"""
+    near, far = torch.chunk(distance, 2, dim)
+    lo, hi = anchor_points - near, anchor_points + far
+    return torch.cat(((lo + hi) / 2, hi - lo), dim) if xywh else torch.cat((lo, hi), dim)
 
 
 def xywh2xyxy(x):
-    """:124-143"""
-    assert x.shape[-1] == 4, f"input shape last dimension expected 4 but input shape is {x.shape}"
-    y = torch.empty_like(x)
-    dw = x[..., 2] / 2
-    dh = x[..., 3] / 2
-    y[..., 0] = x[..., 0] - dw
-    y[..., 1] = x[..., 1] - dh
-    y[..., 2] = x[..., 0] + dw
-    y[..., 3] = x[..., 1] + dh
-    return y
+    """:124-143: centre / size -> corners along the last dimension"""
+    if x.shape[-1] != 4:
+        raise AssertionError(f"input shape last dimension expected 4 but input shape is {x.shape}")
+    centre, half = x[..., :2], x[..., 2:] / 2
+    return torch.cat((centre - half, centre + half), -1)
 
 
 def clip_boxes(boxes, shape):
-    """:240-258 (in place, like the reference)"""
-    boxes[..., 0] = boxes[..., 0].clamp(0, shape[2])
-    boxes[..., 1] = boxes[..., 1].clamp(0, shape[1])
-    boxes[..., 2] = boxes[..., 2].clamp(0, shape[2])
-    boxes[..., 3] = boxes[..., 3].clamp(0, shape[1])
+    """:240-258: clamp xyxy boxes to the image (shape = (C, H, W)), in place like the reference"""
+    boxes[..., 0::2] = boxes[..., 0::2].clamp(0, shape[2])
+    boxes[..., 1::2] = boxes[..., 1::2].clamp(0, shape[1])
     return boxes
 
 
 def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xywh=False):
-    """:203-236"""
-    if ratio_pad is None:
+    """:203-236: undo the letter-box (gain, pad) of img1 -> img0 and clip; for the 640x640 path gain = 1 and pad = (0, 0)"""
+    if ratio_pad is not None:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    else:
         gain = min(img1_shape[0] / img0_shape[1], img1_shape[1] / img0_shape[2])
         pad = (round((img1_shape[1] - img0_shape[2] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[1] * gain) / 2 - 0.1))
-    else:
-        gain = ratio_pad[0][0]
-        pad = ratio_pad[1]
     if padding:
         boxes[..., 0] -= pad[0]
         boxes[..., 1] -= pad[1]
@@ -119,7 +107,7 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xyw
 
 
 def convert_res(data):
-    """:255-258"""
+    """:255-258: (n, 6) detections -> boxes (n, 4), [conf, class] (n, 2)"""
     return data[:, :4], data[:, -2:]
 
 

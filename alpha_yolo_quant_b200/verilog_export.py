@@ -11,26 +11,21 @@ import numpy as np
 
 
 def bit_converter(final_file_name, k, value, element):
-    """utils/save_weights.py:45-71 (kept scalar and literal: it also builds the tables below)"""
+    """The literal format of utils/save_weights.py:45-71: `<sign><width>'b<magnitude bits, zero padded to width>`.
+    width = 18 for a bias, k for a rescale / shift coefficient (never signed), k - 1 for a weight or an activation
+    (sign-magnitude).  A magnitude that does not fit is reported on stdout like the reference does, and printed unpadded."""
     value = int(value)
-    bin_prefix = bin(value).split('b')[0]
-    bin_value = bin(value).split('b')[1]
+    magnitude = format(abs(value), 'b')
     if element == 'bias':
-        zeroes = '0' * (18 - len(bin_value))
-        if 18 - len(bin_value) < 0:
-            print(f'BIAS MORE THAN 18 BIT! {bin_value} {final_file_name}')
-        bin_prefix = bin_prefix[0] + '18' if len(bin_prefix) == 2 else '18'
+        width, signed, what = 18, True, 'BIAS MORE THAN 18 BIT!'
     elif element == 'rescale':
-        zeroes = '0' * (k - len(bin_value))
-        if k - len(bin_value) < 0:
-            print(f'RESCALE MORE THAN {k} BIT! {bin_value} {final_file_name}')
-        bin_prefix = str(k)
+        width, signed, what = k, False, f'RESCALE MORE THAN {k} BIT!'
     else:
-        zeroes = '0' * (k - len(bin_value) - 1)
-        if (k - len(bin_value) - 1) < 0:
-            print(f'MORE THAN {k} BIT! {bin_value} {final_file_name}')
-        bin_prefix = bin_prefix[0] + str(k - 1) if len(bin_prefix) == 2 else str(k - 1)
-    return f"{bin_prefix}'b{zeroes + bin_value}"
+        width, signed, what = k - 1, True, f'MORE THAN {k} BIT!'
+    if len(magnitude) > width:
+        print(f'{what} {magnitude} {final_file_name}')
+    sign = '-' if signed and value < 0 else ''
+    return f"{sign}{width}'b{magnitude.rjust(width, '0')}"
 
 
 def _lines(tag, values, k, element, first_index, final_file_name):
