@@ -519,7 +519,7 @@ struct HeadArgs {
     float* dbox_cls;            // optional (n, 84, A)
 };
 
-__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
+__global__ void __launch_bounds__(128, 8) head_kernel(const HeadArgs a) {
     __shared__ float lexp[512];
     __shared__ int dflw[16];
     const int top = (1 << a.K) - 1;
