@@ -51,3 +51,30 @@ def reduce_max_a(local_max, group=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     vals = t.cpu().tolist()
     return {k: v for k, v in zip(keys, vals)}
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (one rank per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host
+    buffers: first-touch then places them in the local DRAM, so the H2D copies of the ranks do not cross the socket
+    interconnect.  Returns the cpu list it bound to, or None when the topology is not exposed (nothing changes then)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/local_cpulist') as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                lo, hi = part.split('-')
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):
+        return None
+

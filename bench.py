@@ -195,6 +195,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
     torch.cuda.set_device(local)
+    if world > 1:                                                  # host buffers of a rank live next to its GPU (NUMA)
+        from alpha_yolo_quant_b200 import dataparallel as _dp
+        _dp.bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist

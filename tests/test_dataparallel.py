@@ -89,3 +89,14 @@ def test_calibration_text_round_trip():
     out = cal.format_max_a(back)
     assert out == 'start: 1.0\nconv_p2: 1.4271\nconv8: 33.25\n'
     assert parse_max_a(out) == {'start': 1.0, 'conv_p2': 1.4271, 'conv8': 33.25}
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    """no GPU / no sysfs topology -> returns None and leaves the affinity untouched (the bench calls it on every rank)"""
+    import os
+    from alpha_yolo_quant_b200 import dataparallel as dp
+    before = os.sched_getaffinity(0)
+    r = dp.bind_to_gpu_numa_node(0)
+    assert r is None or set(r) <= before
+    if r is None:
+        assert os.sched_getaffinity(0) == before
