@@ -315,6 +315,7 @@ struct TcParams {
     int bw_log, bh_log;            // tile box: 2^bw_log x 2^bh_log x (128 >> (bw_log + bh_log)) pixels (x, y, image)
     int tiles_x, tiles_y, ntiles;
     unsigned mul_x, mul_y;         // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y)  (0 when the divisor is 1)
+    int role_hi;                   // conv_tma: control warps on the highest warp ids (see the kernel)
 };
 
 constexpr int TC_PRODUCERS = 128;

@@ -93,7 +93,14 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 2 * 2 * TMA_NB + 1];   // full[NS], empty[NS], tfull[2][NB], tempty[2][NB], wfull
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // Role of a warp.  The SMSP arbiter favours the highest warp ids, so with role_hi the eight control warps (MMA issuers, TMA
+    // producers: few instructions, but every one of them sits on the tile-to-tile critical path) take the LAST eight warp ids and
+    // the epilogue groups the first ones; `warp` below is the role index (0-1 MMA, 2-5 producers, 8.. epilogue).  The shift is a
+    // multiple of four, so role index and hardware warp id agree modulo 4 (the TMEM lane quarter a warp may read).
+    constexpr int TMA_WARPS = TMA_THREADS / 32;
+    const int hw_warp = tid >> 5;
+    const int warp = tp.role_hi ? (hw_warp + 8 >= TMA_WARPS ? hw_warp + 8 - TMA_WARPS : hw_warp + 8) : hw_warp;
     const int N = a.cout, NS = tp.NS;
     const uint32_t a_slot_bytes = (uint32_t)pl.a_slot_bytes, b_slot_bytes = (uint32_t)pl.slot_chunks * N * 16u;
     unsigned char* sA = smem;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 2 && tp.resident_b) {                               // resident weights: one bulk-TMA burst, still in the prologue
-        if (tid == 64) {
+        if (lane == 0) {
             mbar_init(wfull, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const uint32_t total = (uint32_t)tp.nkc_pad * N * 16u;
@@ -349,7 +356,7 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     int gen_outs = 0;         // MAGIC with a general output list
 };
 
-struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; };
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; int role_hi = 0; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
 template <int FAST>
@@ -435,6 +442,7 @@ static inline void tma_init(TmaState& s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);
+    if (const char* ev = getenv("AYQ_ROLE_HI")) s.role_hi = atoi(ev);
     if (const char* ev = getenv("AYQ_SMEM_KB")) s.budget_kb = atoi(ev);          // experiments: smaller CTAs let consecutive kernels co-reside
     if (const char* ev = getenv("AYQ_RESIDENT_KB")) s.resident_kb = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
     void* fn = nullptr;
@@ -465,6 +473,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.gen_outs = magic && !tma_fast(a) ? 1 : 0;                   // beyond "one identity output (+ phase-split copy)"
     if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, 0)) return 0;
     tc::TcParams& tp = L.tp;
+    tp.role_hi = s.role_hi;
     int bw_log = 4;
     while (bw_log > 0 && (a.Wout % (1 << bw_log))) --bw_log;
     int bh_log = 7 - bw_log;

@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # AYQ_ROLE_PROF=1 (role-level cycle counters of the conv kernel) needs the profiling build of the same sources
-LIB_PATH = os.path.join(HERE, 'libayq_prof.so' if os.environ.get('AYQ_ROLE_PROF') else 'libayq.so')
+LIB_PATH = os.environ.get('AYQ_LIB') or os.path.join(HERE, 'libayq_prof.so' if os.environ.get('AYQ_ROLE_PROF') else 'libayq.so')
 MAX_DET, DET_STRIDE, ANCHORS = 300, 6, 8400
 
 _c = ctypes

@@ -380,6 +380,111 @@ def capture_goldens_float(work, pkg_root, k, images_u8):
     return out
 
 
+def crafted_predictions():
+    """Hand-made (84, 8400) prediction tensors for the q_NMS corner cases the forward goldens never reach:
+    more than 300 kept rows (`i[:max_det]`, stage_8_torch_full_quant.py:354), more than 1000 candidates with > 300 survivors,
+    exactly 300 / 301 survivors, heavy score ties.  Integer valued like the reference's dbox_cls: xywh in 412.1635-per-pixel
+    units, class scores 0..32767.  Stored compactly as (dbox int32 (4,8400), score_max int32, score_arg int16)."""
+    A = 8400
+    rng = np.random.default_rng(2024)
+    cases = {}
+
+    def grid_case(n_boxes, cols, pitch_px, size_px, score_fn, cls_fn, jitter=0):
+        d = np.zeros((4, A), np.int32)
+        sm = np.zeros(A, np.int32)
+        sa = np.zeros(A, np.int16)
+        idx = rng.permutation(A)[:n_boxes]
+        idx.sort()
+        for q, a in enumerate(idx):
+            cx = (8 + pitch_px * (q % cols)) * 412 + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0)
+            cy = (8 + pitch_px * (q // cols)) * 412 + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0)
+            d[:, a] = (cx, cy, size_px * 412, size_px * 412)
+            sm[a] = score_fn(q)
+            sa[a] = cls_fn(q)
+        return d, sm, sa
+
+    # A: 420 separated boxes of ONE class, distinct scores -> 420 survivors, the first 300 are returned
+    cases['keep420_distinct'] = grid_case(420, 40, 15, 10, lambda q: 32000 - 7 * q, lambda q: 3)
+    # B: 1500 candidates of one class on a 50-column grid, scores from a set of 25 values (ties), boxes separated -> top-1000 cut, then 300
+    cases['cand1500_ties'] = grid_case(1500, 50, 12, 8, lambda q: 9000 + 100 * (q * 7 % 25), lambda q: 11)
+    # C / D: exactly 300 and 301 separated boxes (the boundary of the cap), mixed classes (class offset j * 7680 shifts the boxes)
+    cases['keep300_exact'] = grid_case(300, 30, 20, 9, lambda q: 20000 + 3 * q, lambda q: q % 80)
+    cases['keep301'] = grid_case(301, 30, 20, 9, lambda q: 20000 + 3 * (q % 97), lambda q: (q * 5) % 80)
+    # E: dense overlapping field, 3000 candidates, jittered boxes of 60 px on a 6 px pitch, 40 tied score levels
+    cases['dense3000'] = grid_case(3000, 100, 6, 60, lambda q: 8200 + 13 * (q * 11 % 40), lambda q: q % 3, jitter=300)
+    # F: 8400 candidates, every anchor a small separated box (100 x 84 grid on a 7 px pitch): > 300 survivors out of the top 1000
+    cases['all8400'] = grid_case(8400, 100, 7, 5, lambda q: 8193 + (q * 2654435761 % 20000), lambda q: (q // 7) % 80)
+    return cases
+
+
+def capture_nms_extra(work, pkg_root, k, n_images):
+    """(1) crafted predictions through the UNMODIFIED coord_quant() + the forward() tail (scale_boxes / convert_res), with
+    argsort(stable=True) forced (the pinned order) AND exactly as shipped (torch's default argsort) -> golden_nms_k{K}.npz;
+    (2) the forward goldens' images once more with the shipped argsort, to report how often the reference as users run it
+    differs from the pinned order (SURVEY hard part 3)."""
+    g = run_stage(pkg_root, 'stage_8_torch_full_quant.py')
+    model = g['model']
+    fwd_globals = g['silu'].__globals__
+    coord_quant, scale_boxes, convert_res = g['coord_quant'], g['scale_boxes'], g['convert_res']
+    real_argsort = torch.Tensor.argsort
+
+    def tail(pred, stable):
+        """forward() :1265-1275 on a prediction tensor"""
+        def stable_argsort(self, *a, **kw):
+            kw['stable'] = True
+            return real_argsort(self, *a, **kw)
+        if stable:
+            torch.Tensor.argsort = stable_argsort
+        try:
+            res = coord_quant(pred.clone())
+        finally:
+            torch.Tensor.argsort = real_argsort
+        if res is None:
+            return np.zeros((0, 4), np.float32), np.zeros((0, 2), np.float32)
+        for i, p_ in enumerate(res):                                  # :1267-1270 with orig_img (1, 3, 640, 640)
+            p_[:, :4] = scale_boxes((640, 640), p_[:, :4], (3, 640, 640))
+        b, c = convert_res(p_)
+        return b.numpy().astype(np.float32), c.numpy().astype(np.float32)
+
+    out = {}
+    names = []
+    for name, (d, sm, sa) in crafted_predictions().items():
+        pred = torch.zeros((1, 84, 8400), dtype=torch.float32)
+        pred[0, :4] = torch.from_numpy(d.astype(np.float32))
+        pred[0, 4 + torch.from_numpy(sa.astype(np.int64)), torch.arange(8400)] = torch.from_numpy(sm.astype(np.float32))
+        bs, cs = tail(pred, True)
+        bu, cu = tail(pred, False)
+        out[f'{name}/dbox'] = d
+        out[f'{name}/score_max'] = sm
+        out[f'{name}/score_arg'] = sa
+        out[f'{name}/boxes'] = bs
+        out[f'{name}/classes'] = cs
+        out[f'{name}/boxes_unpatched'] = bu
+        out[f'{name}/classes_unpatched'] = cu
+        names.append(name)
+        same = bs.shape == bu.shape and np.array_equal(bs, bu) and np.array_equal(cs, cu)
+        print(f'[harness] crafted {name}: ncand={(sm > 8192).sum()} kept(stable)={len(bs)} kept(unpatched)={len(bu)} identical={same}')
+    out['cases'] = np.array(names)
+    # forward goldens with the shipped argsort
+    state = {}
+    real_coord_quant = g['coord_quant']
+
+    def cq(pred):
+        state['pred'] = pred.clone()
+        return real_coord_quant(pred)
+    fwd_globals['coord_quant'] = cq
+    for i in range(n_images):
+        x = synth.to_input_tensor(synth.synth_image_u8(i))
+        with torch.no_grad():
+            boxes, classes = model(x)
+        out[f'img{i}_boxes_unpatched'] = np.zeros((0, 4), np.float32) if boxes is None else boxes.numpy().astype(np.float32)
+        out[f'img{i}_classes_unpatched'] = np.zeros((0, 2), np.float32) if classes is None else classes.numpy().astype(np.float32)
+        print(f'[harness] image {i} with the shipped argsort: ndet={len(out[f"img{i}_boxes_unpatched"])}')
+    out['n_images'] = np.array(n_images)
+    out['versions'] = np.array(f'torch {torch.__version__} numpy {np.__version__}')
+    return out
+
+
 def capture_weight_quant(work, pkg_root, k, layers):
     """Run the UNMODIFIED stage_6_full_quant.py (text dumps silenced exactly as in run_pipeline) under a profile hook and
     record, for the chosen layers, the arguments and results of conv_quant() (stage_6_full_quant.py:89-126):
@@ -469,6 +574,11 @@ def main():
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
     ap.add_argument('--weight-quant', default='', metavar='LAYERS',
                     help='only record conv_quant() goldens of stage_6_full_quant.py for these comma-separated layers')
+    ap.add_argument('--export-main-dir', action='store_true',
+                    help='only pack the files the hot path reads, AS THE REFERENCE WROTE THEM (stage_7.py:780 torch.save state_dict, '
+                         'utils/save_weights.py:24-30 gzip-pickle bias_scales/, stage_5 max_a.txt), into main_dir_k{K}.tar.xz')
+    ap.add_argument('--nms-extra', action='store_true',
+                    help='only record the crafted q_NMS corner cases and the shipped-argsort detections -> golden_nms_k{K}.npz')
     ap.add_argument('--float-head', type=int, default=0, metavar='N',
                     help='only record stage_8_torch.py (float head) goldens for N images -> golden_float_k{K}.npz')
     args = ap.parse_args()
@@ -492,6 +602,21 @@ def main():
         gold = capture_weight_quant(work, pkg_root, k, set(args.weight_quant.split(',')))
         np.savez_compressed(os.path.join(args.out, f'golden_wquant_k{k}.npz'), **gold)
         print('[harness] wrote weight-quantiser goldens:', list(gold['layers']))
+        return
+    if args.export_main_dir:
+        import tarfile
+        main_dir = f'{k}_nano'
+        dst = os.path.join(args.out, f'main_dir_k{k}.tar.xz')
+        with tarfile.open(dst, 'w:xz') as tf:
+            tf.add(os.path.join(main_dir, 'results', f'QUANT_WEIGHTS_{k}.pickle'))
+            tf.add(os.path.join(main_dir, 'results', 'max_a.txt'))
+            tf.add(os.path.join(main_dir, 'bias_scales'))
+        print('[harness] wrote', dst, os.path.getsize(dst), 'bytes')
+        return
+    if args.nms_extra:
+        gold = capture_nms_extra(work, pkg_root, k, args.n_golden)
+        np.savez_compressed(os.path.join(args.out, f'golden_nms_k{k}.npz'), **gold)
+        print('[harness] wrote q_NMS corner-case goldens to', args.out)
         return
     if args.float_head:
         images = [synth.synth_image_u8(s) for s in range(args.float_head)]
