@@ -15,6 +15,8 @@ LIB = os.path.join(HERE, 'libayq.so')
 STAMP = os.path.join(HERE, '.libayq.stamp')
 LIB_PROF = os.path.join(HERE, 'libayq_prof.so')        # same sources with -DAYQ_ROLE_PROF_BUILD (role-level cycle counters)
 STAMP_PROF = os.path.join(HERE, '.libayq_prof.stamp')
+LIB_TEST = os.path.join(HERE, 'libayq_test.so')        # same sources with -DAYQ_TEST_BUILD: + the dp4a / cp.async-fed cross-check conv kernels
+STAMP_TEST = os.path.join(HERE, '.libayq_test.stamp')
 SOURCES = ['ayq.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--fmad=false',            # the reference multiplies and adds in separate fp32 ops (SURVEY hard part 1)
@@ -39,13 +41,15 @@ def nvcc_path():
     return 'nvcc'
 
 
-def build(force=False, verbose=False, prof=False):
-    """prof=True builds the profiling variant libayq_prof.so (AYQ_ROLE_PROF=1 loads it instead of libayq.so)."""
+def build(force=False, verbose=False, prof=False, test=False):
+    """prof=True builds the profiling variant libayq_prof.so (AYQ_ROLE_PROF=1 loads it instead of libayq.so); test=True builds
+    libayq_test.so, the product sources plus the two cross-check convolution families (tests only, never the product path)."""
     dig = _digest()
-    lib, stamp = (LIB_PROF, STAMP_PROF) if prof else (LIB, STAMP)
+    lib, stamp = (LIB_PROF, STAMP_PROF) if prof else ((LIB_TEST, STAMP_TEST) if test else (LIB, STAMP))
     if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return lib
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-DAYQ_ROLE_PROF_BUILD'] if prof else []) + (['-Xptxas', '-v'] if verbose else []) + \
+    cmd = [nvcc_path()] + NVCC_FLAGS + (['-DAYQ_ROLE_PROF_BUILD'] if prof else []) + (['-DAYQ_TEST_BUILD'] if test else []) + \
+          (['-Xptxas', '-v'] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ['-o', lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -58,4 +62,4 @@ def build(force=False, verbose=False, prof=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, prof='--prof' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, prof='--prof' in sys.argv, test='--test' in sys.argv))

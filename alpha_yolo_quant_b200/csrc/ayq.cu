@@ -66,6 +66,11 @@ struct ayq_engine {
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_d2h[2]{};
     int host_cap = 0;
     bool host_u8 = false;
+    long long host_passes = 0;             // passes the host pipeline has enqueued so far (slot = host_passes & 1; persists across async calls)
+    // cross-entry ordering: every entry point records `ev_busy` on the stream it launched on and waits for it first, so that
+    // two calls on different streams (or a device entry followed by the host pipeline) never share the workspace concurrently
+    cudaEvent_t ev_busy = nullptr;
+    bool busy_recorded = false;
     // profiling
     bool profiling = false;
     std::vector<float> op_ms;
@@ -82,11 +87,23 @@ struct ayq_engine {
     long long* d_role = nullptr;
     TcState tc;                            // tcgen05 path state
     TmaState tma;                          // TMA-fed tcgen05 path: driver entry point for tensor-map encoding
+    std::vector<int> conv_impl_used;       // per op: implementation that ran it in the last pass (ayq_get_conv_impls)
     std::vector<TmaLaunch> tma_cache;      // per op: tensor maps + stage plan for the last pass size
     std::vector<std::vector<TmaSeg>> tma_segs;   // per op: source buffers of the conv input
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The engine owns ONE workspace: entries on different streams are ordered through ev_busy (see ayq.h "stream semantics").
+static int wait_busy(ayq_engine* e, cudaStream_t st) {
+    if (e->busy_recorded) CK(cudaStreamWaitEvent(st, e->ev_busy, 0));
+    return 0;
+}
+static int mark_busy(ayq_engine* e, cudaStream_t st) {
+    CK(cudaEventRecord(e->ev_busy, st));
+    e->busy_recorded = true;
+    return 0;
+}
 static inline float f_from_bits(int32_t b) { float f; memcpy(&f, &b, 4); return f; }
 
 extern "C" const char* ayq_last_error(void) { return g_err.c_str(); }
@@ -94,6 +111,7 @@ extern "C" int ayq_version(void) { return AYQ_PLAN_VERSION; }
 
 static void drop_graphs(ayq_engine* e);
 static void free_workspace(ayq_engine* e) {
+    if (e->ws) cudaDeviceSynchronize();                            // asynchronous host calls may still be using it
     drop_graphs(e);
     if (e->ws) cudaFree(e->ws);
     e->ws = nullptr; e->ws_bytes = 0; e->cap = 0;
@@ -104,8 +122,16 @@ static void free_workspace(ayq_engine* e) {
     tc_release(e->tc);
 }
 
+static int ensure_workspace_impl(ayq_engine* e, int n);
+static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a);
+static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a);
 static int ensure_workspace(ayq_engine* e, int n) {
     if (n <= e->cap) return 0;
+    const int rc = ensure_workspace_impl(e, n);
+    if (rc) free_workspace(e);                                     // never leave a half-built workspace behind (cap stays 0)
+    return rc;
+}
+static int ensure_workspace_impl(ayq_engine* e, int n) {
     free_workspace(e);
     const int cap = n;
     size_t off = 0;
@@ -172,16 +198,24 @@ static int ensure_workspace(ayq_engine* e, int n) {
         }
     }
     (void)ntaps;
+    // No fallback in the conv path: every convolution of the plan must be covered by the TMA-fed tcgen05 kernel.  Checked here,
+    // when the workspace (and with it the tensor maps) is built, so that an uncovered shape is a load-time error.
+    if (e->conv_impl == 2) {
+        e->cap = cap;
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            if (e->ops[i].f[0] != OP_CONV) continue;
+            ConvArgs a;
+            build_conv_args(e, (int)i, cap, a);
+            if (!prepare_tma_conv(e, (int)i, cap, a))
+                return fail(-38, "conv op %zu (%s): shape not covered by the TMA-fed tcgen05 kernel (cout %d, %dx%d, stride %d, %d K chunks)", i,
+                            (const char*)(e->host_data.data() + e->ops[i].f[CF_NAME_OFF]), a.cout, a.Hout, a.Wout, a.stride, a.nkc);
+        }
+    }
     return 0;
 }
 
 extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_handle* out) {
     if (!plan_blob || !out || nbytes < sizeof(PlanHeader)) return fail(-22, "ayq_create: bad arguments");
-    int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    if (ce != cudaSuccess || ndev <= 0)
-        return fail(-19, "ayq_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
-    if (device < 0 || device >= ndev) return fail(-22, "ayq_create: device %d out of range (%d devices)", device, ndev);
     const unsigned char* p = (const unsigned char*)plan_blob;
     PlanHeader h;
     memcpy(&h, p, sizeof h);
@@ -191,11 +225,69 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     if (h.data_off + h.data_bytes > nbytes || h.ops_off + (uint64_t)h.n_ops * sizeof(OpDesc) > nbytes ||
         h.bufs_off + (uint64_t)h.n_bufs * sizeof(BufDesc) > nbytes)
         return fail(-22, "ayq_create: truncated plan (%zu bytes)", nbytes);
+    // ---- validate everything the kernels will index with before any of it is used (a blob from another compiler version or
+    // a corrupted file must be rejected here, not read out of bounds on the device)
+    if (h.img_h != 640 || h.img_w != 640 || h.n_anchors != 8400)
+        return fail(-22, "ayq_create: plan is for %dx%d images / %d anchors; the Detect-head kernels are built for 640x640 / 8400", h.img_h, h.img_w, h.n_anchors);
+    if (h.n_bufs < 1 || h.n_bufs > 4096 || h.n_ops < 1 || h.n_ops > 4096) return fail(-22, "ayq_create: implausible plan (%d buffers, %d ops)", h.n_bufs, h.n_ops);
+    {
+        const OpDesc* ops = (const OpDesc*)(p + h.ops_off);
+        const BufDesc* bufs = (const BufDesc*)(p + h.bufs_off);
+        const unsigned char* data = p + h.data_off;
+        const uint64_t DB = h.data_bytes;
+        auto in_data = [&](int64_t off, uint64_t bytes) { return off >= 0 && (uint64_t)off <= DB && bytes <= DB - (uint64_t)off; };
+        auto buf_ok = [&](int b) { return b >= 0 && b < h.n_bufs; };
+        for (int b = 0; b < h.n_bufs; ++b)
+            if (bufs[b].nplanes < 1 || bufs[b].H < 1 || bufs[b].W < 1 || bufs[b].H > 4096 || bufs[b].W > 4096 || (bufs[b].elem_bytes != 1 && bufs[b].elem_bytes != 2 && bufs[b].elem_bytes != 4))
+                return fail(-22, "ayq_create: buffer %d has a bad descriptor", b);
+        for (int i = 0; i < h.n_ops; ++i) {
+            const int32_t* f = ops[i].f;
+            bool ok = true;
+            if (f[0] == OP_CONV) {
+                const int nkc = f[CF_NKC], cout = f[CF_COUT], nkp = (nkc + 1) & ~1;
+                ok = nkc >= 1 && nkc <= 4096 && cout >= 16 && cout <= 256 && cout % 16 == 0 && (f[CF_KSIZE] == 1 || f[CF_KSIZE] == 3) &&
+                     (f[CF_STRIDE] == 1 || f[CF_STRIDE] == 2) && f[CF_NOUT] >= 1 && f[CF_NOUT] <= AYQ_MAX_OUT && f[CF_EPI] >= 0 && f[CF_EPI] <= 2 &&
+                     in_data(f[CF_KC_OFF], (uint64_t)nkc * 16) && in_data(f[CF_W_OFF], (uint64_t)nkp * cout * 16) && in_data(f[CF_BIAS_OFF], (uint64_t)cout * 4) &&
+                     in_data(f[CF_TAB_OFF], (uint64_t)cout * 16) && in_data(f[CF_NAME_OFF], 1) &&
+                     (f[CF_EPI] != EPI_SILU || in_data(f[CF_LUT_OFF], (uint64_t)(2 * f[CF_CLAMP] + 1) * 4)) && (f[CF_ACC_BUF] < 0 || buf_ok(f[CF_ACC_BUF]));
+                if (ok) {
+                    const int32_t* kc = (const int32_t*)(data + f[CF_KC_OFF]);
+                    for (int k = 0; k < nkc && ok; ++k)
+                        ok = buf_ok(kc[4 * k]) && kc[4 * k + 1] >= 0 && kc[4 * k + 1] < bufs[kc[4 * k]].nplanes && kc[4 * k + 2] >= 0 && kc[4 * k + 2] < f[CF_KSIZE] &&
+                             kc[4 * k + 3] >= 0 && kc[4 * k + 3] < f[CF_KSIZE];
+                    for (int o = 0; o < f[CF_NOUT] && ok; ++o) {
+                        const int32_t* of = f + CF_OUT0 + CF_OUT_STRIDE * o;
+                        ok = buf_ok(of[0]) && of[1] >= 0 && of[5] >= 0 && of[5] <= 2;
+                    }
+                    if (ok && memchr(data + f[CF_NAME_OFF], 0, (size_t)(DB - (uint64_t)f[CF_NAME_OFF])) == nullptr) ok = false;
+                }
+            } else if (f[0] == OP_CONV_P1) {
+                ok = buf_ok(f[P1_OUT_BUF]) && in_data(f[P1_W_OFF], 16 * 32) && in_data(f[P1_BIAS_OFF], 64) && in_data(f[P1_TAB_OFF], 256) &&
+                     in_data(f[P1_LUT_OFF], (uint64_t)(2 * f[P1_CLAMP] + 1) * 4);
+            } else if (f[0] == OP_POOL) {
+                ok = buf_ok(f[PL_IN_BUF]) && buf_ok(f[PL_OUT_BUF]) && f[PL_NPLANES] >= 1 && f[PL_H] >= 1 && f[PL_W] >= 1;
+            } else if (f[0] == OP_HEAD) {
+                for (int l = 0; l < 3; ++l) ok = ok && buf_ok(f[HD_BOX_BUF0 + l]) && buf_ok(f[HD_CLS_BUF0 + l]);
+                ok = ok && in_data(f[HD_LUT_EXP_OFF], (uint64_t)(1u << h.K) * 4) && in_data(f[HD_LUT16_OFF], 65535 * 2) && in_data(f[HD_LO16_OFF], 65535 * 2) &&
+                     in_data(f[HD_DFLW_OFF], 64) && in_data(f[HD_ANCH_OFF], (uint64_t)h.n_anchors * 8);
+            } else if (f[0] == OP_HEAD_FLOAT) {
+                for (int l = 0; l < 3; ++l) ok = ok && buf_ok(f[HF_BOX_BUF0 + l]) && buf_ok(f[HF_CLS_BUF0 + l]);
+                ok = ok && in_data(f[HF_BOX_SCALE_OFF], 3 * 64 * 4) && in_data(f[HF_CLS_SCALE_OFF], 3 * 80 * 4) && in_data(f[HF_DFLW_OFF], 64);
+            } else if (f[0] != OP_NMS && f[0] != OP_NMS_FLOAT) ok = false;
+            if (!ok) return fail(-22, "ayq_create: plan op %d (kind %d) references data outside the blob or an unknown buffer", i, f[0]);
+        }
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(-19, "ayq_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(-22, "ayq_create: device %d out of range (%d devices)", device, ndev);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(-19, "ayq_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     ayq_engine* e = new ayq_engine();
+    struct Guard { ayq_engine* e; ~Guard() { if (e) { if (e->d_data) cudaFree(e->d_data); if (e->ev_busy) cudaEventDestroy(e->ev_busy); if (e->d_role) cudaFree(e->d_role); delete e; } } } guard{e};
     e->device = device;
     e->hdr = h;
     e->bufs.resize(h.n_bufs);
@@ -204,20 +296,20 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     memcpy(e->ops.data(), p + h.ops_off, sizeof(OpDesc) * h.n_ops);
     e->host_data.assign(p + h.data_off, p + h.data_off + h.data_bytes);
     if (cudaMalloc(&e->d_data, h.data_bytes) != cudaSuccess ||
-        cudaMemcpy(e->d_data, e->host_data.data(), h.data_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-        delete e;
+        cudaMemcpy(e->d_data, e->host_data.data(), h.data_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(-12, "ayq_create: cannot upload %llu bytes of plan data", (unsigned long long)h.data_bytes);
-    }
+    CK(cudaEventCreateWithFlags(&e->ev_busy, cudaEventDisableTiming));
+#ifdef AYQ_TEST_BUILD
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#endif
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
-    if (h.n_anchors < 1 || h.n_anchors > NMS_SORT_N) { delete e; return fail(-22, "ayq_create: %d anchors (1..%d)", h.n_anchors, NMS_SORT_N); }
     CK(cudaFuncSetAttribute(nms_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nmsf_smem_bytes(h.n_anchors)));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
     e->role_prof = getenv("AYQ_ROLE_PROF") != nullptr;
 #ifndef AYQ_ROLE_PROF_BUILD
-    if (e->role_prof) { delete e; return fail(-22, "AYQ_ROLE_PROF=1 needs the profiling build of the library (libayq_prof.so: python -m alpha_yolo_quant_b200.build --prof)"); }
+    if (e->role_prof) { return fail(-22, "AYQ_ROLE_PROF=1 needs the profiling build of the library (libayq_prof.so: python -m alpha_yolo_quant_b200.build --prof)"); }
 #endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
@@ -228,8 +320,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     }
     if (e->role_prof) {
         e->use_graph = false;
-        cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16);
-        cudaMemset(e->d_role, 0, sizeof(long long) * h.n_ops * 148 * 16);
+        CK(cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16));
+        CK(cudaMemset(e->d_role, 0, sizeof(long long) * h.n_ops * 148 * 16));
     }
     g_pdl = getenv("AYQ_NO_PDL") == nullptr ? 1 : 0;
     tc_init(e->tc);
@@ -248,6 +340,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     }
     e->op_ms.assign(h.n_ops + 1, 0.f);
     e->op_calls.assign(h.n_ops + 1, 0);
+    e->conv_impl_used.assign(h.n_ops, -1);
+    guard.e = nullptr;                                             // success: the caller owns the engine now
     *out = e;
     return 0;
 }
@@ -295,6 +389,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->s_cap) cudaStreamDestroy(e->s_cap);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    if (e->ev_busy) cudaEventDestroy(e->ev_busy);
     delete e;
     return 0;
 }
@@ -307,6 +402,10 @@ extern "C" int ayq_set_max_batch(ayq_handle e, int max_batch) {
 extern "C" size_t ayq_workspace_bytes(ayq_handle e) { return e ? e->ws_bytes : 0; }
 extern "C" int ayq_set_conv_impl(ayq_handle e, int impl) {
     if (!e || impl < 0 || impl > 2) return fail(-22, "ayq_set_conv_impl: 0 (dp4a), 1 (tcgen05, cp.async feed) or 2 (tcgen05, TMA feed)");
+#ifndef AYQ_TEST_BUILD
+    if (impl != 2) return fail(-38, "ayq_set_conv_impl: this is the product library, which contains the TMA-fed tcgen05 convolution only; "
+                                    "the dp4a / cp.async cross-check kernels live in the test build (libayq_test.so)");
+#endif
     if (e->conv_impl != impl) drop_graphs(e);
     e->conv_impl = impl;
     return 0;
@@ -328,15 +427,21 @@ extern "C" int ayq_get_op_times(ayq_handle e, float* ms, int32_t* calls, int cap
     for (int i = 0; i < n && i < cap; ++i) { ms[i] = e->op_ms[i]; calls[i] = e->op_calls[i]; }
     return n;
 }
+extern "C" int ayq_get_conv_impls(ayq_handle e, int32_t* impl, int cap) {
+    if (!e || !impl) return fail(-22, "ayq_get_conv_impls: bad arguments");
+    const int n = (int)e->ops.size();
+    for (int i = 0; i < n && i < cap; ++i)
+        impl[i] = e->ops[i].f[0] == OP_CONV ? (i < (int)e->conv_impl_used.size() ? e->conv_impl_used[i] : -1) : -2;
+    return n < cap ? n : cap;
+}
 extern "C" int ayq_launches_per_pass(ayq_handle e) {
     if (!e) return fail(-22, "null handle");
     return (int)e->ops.size() + 1;          // + the abs-max reduction; the memset node is not a kernel
 }
 
 // ---- one pass over n <= cap images ---------------------------------------------------------------------
-static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
+static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a) {
     const int32_t* f = e->ops[opi].f;
-    ConvArgs a;
     memset(&a, 0, sizeof a);
     a.kc = e->d_kc[opi];
     a.nkc = f[CF_NKC];
@@ -362,24 +467,41 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     if (f[CF_ACC_BUF] >= 0) a.acc_tap = (int*)(e->ws + e->buf_off[f[CF_ACC_BUF]]);   // raw accumulators feed the float head
     a.half = 0.5f;
     a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * 16 : nullptr;
+}
+// tensor maps + stage plan of conv op `opi` for passes of n images (cached); returns L.ok
+static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {
+    const int32_t* f = e->ops[opi].f;
+    TmaLaunch& L = e->tma_cache[opi];
+    const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
+    const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
+    if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
+                              (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
+    return L.ok;
+}
+static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
+    const int32_t* f = e->ops[opi].f;
+    ConvArgs a;
+    build_conv_args(e, opi, n, a);
     if (e->conv_impl == 2) {
+        prepare_tma_conv(e, opi, n, a);
         TmaLaunch& L = e->tma_cache[opi];
-        const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
-        const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
-        if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
-                                  (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
         if (L.ok) {
-            if (tma_launch(L, a, st) == 0) return 0;
+            if (tma_launch(L, a, st) == 0) { e->conv_impl_used[opi] = 2; return 0; }
             return fail(-5, "TMA conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
         }
-        // shape not covered by the TMA kernel -> cp.async-fed tcgen05 kernel below
+        // no silent fallback: a shape the TMA kernel does not cover is an error (ensure_workspace checks every conv op up front)
+        return fail(-38, "conv op %d (%s): shape not covered by the TMA-fed tcgen05 kernel", opi, (const char*)(e->host_data.data() + f[CF_NAME_OFF]));
     }
+#ifndef AYQ_TEST_BUILD
+    return fail(-38, "conv op %d: no kernel family selected", opi);
+#else
     if (e->conv_impl >= 1) {
         int rc = tc_launch_conv(e->tc, a, e->h_kc[opi].data(), (const float*)(e->host_data.data() + f[CF_TAB_OFF]), (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), st);
-        if (rc == 0) return 0;
+        if (rc == 0) { e->conv_impl_used[opi] = 1; return 0; }
         if (rc != 1) return fail(-5, "tcgen05 conv launch failed for op %d: %s", opi, cudaGetErrorString(cudaGetLastError()));
         // rc == 1: shape not covered by the tcgen05 kernel -> CUDA-core kernel below
     }
+    e->conv_impl_used[opi] = 0;
     const size_t npix = (size_t)n * a.Hout * a.Wout;
     const unsigned gx = (unsigned)((npix + 127) / 128);
     const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 4 : 0;       // the sigmoid table is only read by the SiLU epilogue
@@ -389,6 +511,7 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
         CK(launch_k(conv_dp4a_kernel<16>, dim3(gx, a.cout / 16), dim3(128), (size_t)a.nkc * 16 * 16 + lut_bytes, st, a));
     }
     return 0;
+#endif
 }
 
 struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; };
@@ -438,7 +561,12 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                           magic_coeffs_ok(16, a.M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
         if (lean) {                                                // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
             for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }
-            if (e->conv_impl >= 1 && !e->p1_dp4a) {                // tensor-core Conv_P1 (conv_tc.cuh): per-parity weight matrices with the byte shift
+#ifdef AYQ_TEST_BUILD
+            const bool p1_tc = e->conv_impl >= 1 && !e->p1_dp4a;
+#else
+            const bool p1_tc = true;                               // product library: the tensor-core Conv_P1 only
+#endif
+            if (p1_tc) {                                           // tensor-core Conv_P1 (conv_tc.cuh): per-parity weight matrices with the byte shift
                 tc::P1B wb;
                 memset(&wb, 0, sizeof wb);
                 for (int par = 0; par < 2; ++par)
@@ -448,8 +576,11 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                                 wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
                 if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
                 else CK(launch_k(tc::conv_p1_tc_kernel<false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
-            } else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
+            }
+#ifdef AYQ_TEST_BUILD
+            else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
             else CK(launch_k(conv_p1_fast_kernel<false>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
+#endif
         } else if (pa.img_u8) CK(launch_k(conv_p1_kernel<true>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, nz), dim3(256), 0, st, a, pc));
         else CK(launch_k(conv_p1_kernel<false>, dim3((a.Wout + P1_TW - 1) / P1_TW, (a.Hout + P1_TH - 1) / P1_TH, nz), dim3(256), 0, st, a, pc));
         break;
@@ -623,14 +754,16 @@ extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cl
     const int mb = e->max_batch;
     int rc = ensure_workspace(e, n < mb ? n : mb);
     if (rc) return rc;
+    rc = wait_busy(e, st);                                         // a pass of another stream / the host pipeline may own the workspace
+    if (rc) return rc;
     const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
     for (int i0 = 0; i0 < n; i0 += mb) {
         const int m = (n - i0) < mb ? (n - i0) : mb;
         rc = run_pass(e, img + (size_t)i0 * img_elems, nullptr, m, dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
                       dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, counts + i0, st);
-        if (rc) return rc;
+        if (rc) { mark_busy(e, st); return rc; }
     }
-    return 0;
+    return mark_busy(e, st);
 }
 
 // ---- host-buffer entry: double-buffered H2D / compute / D2H --------------------------------------------
@@ -665,7 +798,19 @@ static int ensure_host_pipeline(ayq_engine* e, int m, bool u8) {
     return 0;
 }
 
-static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n, float* dets_host, int32_t* counts_host) {
+static int host_sync(ayq_engine* e) {
+    cudaError_t r0 = e->s_d2h ? cudaStreamSynchronize(e->s_d2h) : cudaSuccess;
+    cudaError_t r1 = e->s_copy ? cudaStreamSynchronize(e->s_copy) : cudaSuccess;
+    cudaError_t r2 = e->s_comp ? cudaStreamSynchronize(e->s_comp) : cudaSuccess;
+    const cudaError_t r = r0 != cudaSuccess ? r0 : (r1 != cudaSuccess ? r1 : r2);
+    if (r != cudaSuccess) return fail(-5, "host pipeline failed: %s", cudaGetErrorString(r));
+    return 0;
+}
+
+// Enqueues the whole call on the engine's three streams (H2D | kernels | D2H) and returns; `sync` waits for the results.
+// Slots, events and the pass counter persist across calls, so a second asynchronous call queued behind the first overlaps its
+// first H2D with the first call's last pass (nothing but the very first copy and the very last pass of a SEQUENCE is exposed).
+static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n, float* dets_host, int32_t* counts_host, bool sync) {
     if (!e || !img_host || !dets_host || !counts_host || n < 0) return fail(-22, "ayq_forward_host: bad arguments");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
@@ -696,42 +841,68 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
         for (; rem > 0; rem -= mb) sizes.push_back(rem < mb ? rem : mb);
         for (auto it = tail.rbegin(); it != tail.rend(); ++it) sizes.push_back(*it);
     }
-    int rc = ensure_workspace(e, n < e->max_batch ? n : e->max_batch);
+    if (m_max > e->cap || m_max > e->host_cap || (u8 && !e->d_img_u8[0])) {   // (re)allocation: nothing may be in flight
+        int rc = host_sync(e);
+        if (rc) return rc;
+    }
+    int rc = ensure_workspace(e, m_max);                           // the passes of this entry are at most m_max images
     if (rc) return rc;
     rc = ensure_host_pipeline(e, m_max, u8);
     if (rc) return rc;
-    const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
-    int slot = 0, pass = 0;
-    int i0 = 0;
-    for (size_t pi = 0; pi < sizes.size(); i0 += sizes[pi], ++pi, ++pass, slot ^= 1) {
-        const int m = sizes[pi];
-        // three streams: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i
-        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));   // d_img[slot] still being read
-        if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
-        else CK(cudaMemcpyAsync(e->d_img[slot], (const float*)img_host + (size_t)i0 * img_elems, img_elems * m * sizeof(float), cudaMemcpyHostToDevice, e->s_copy));
-        CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
-        CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
-        if (pass >= 2) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));    // d_dets[slot] still draining
-        rc = run_pass(e, u8 ? nullptr : e->d_img[slot], u8 ? e->d_img_u8[slot] : nullptr, m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
-        if (rc) return rc;
-        CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
-        CK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[slot], 0));
-        CK(cudaMemcpyAsync(dets_host + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, e->d_dets[slot],
-                           (size_t)m * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
-        CK(cudaMemcpyAsync(counts_host + i0, e->d_counts[slot], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
-        CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
+    if (e->busy_recorded) {                                        // a device-entry pass on a caller's stream may own the workspace
+        CK(cudaStreamWaitEvent(e->s_comp, e->ev_busy, 0));
+        CK(cudaStreamWaitEvent(e->s_copy, e->ev_busy, 0));
     }
-    CK(cudaStreamSynchronize(e->s_d2h));
-    CK(cudaStreamSynchronize(e->s_copy));
-    CK(cudaStreamSynchronize(e->s_comp));
-    return 0;
+    const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
+    int i0 = 0;
+    auto enqueue = [&]() -> int {
+        for (size_t pi = 0; pi < sizes.size(); i0 += sizes[pi], ++pi, ++e->host_passes) {
+            const int m = sizes[pi];
+            const int slot = (int)(e->host_passes & 1);
+            const bool reuse = e->host_passes >= 2;
+            // three streams: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i
+            if (reuse) CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));   // d_img[slot] still being read
+            if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
+            else CK(cudaMemcpyAsync(e->d_img[slot], (const float*)img_host + (size_t)i0 * img_elems, img_elems * m * sizeof(float), cudaMemcpyHostToDevice, e->s_copy));
+            CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
+            CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
+            if (reuse) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));    // d_dets[slot] still draining
+            int prc = run_pass(e, u8 ? nullptr : e->d_img[slot], u8 ? e->d_img_u8[slot] : nullptr, m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
+            if (prc) return prc;
+            CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
+            CK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[slot], 0));
+            CK(cudaMemcpyAsync(dets_host + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, e->d_dets[slot],
+                               (size_t)m * AYQ_MAX_DET * AYQ_DET_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+            CK(cudaMemcpyAsync(counts_host + i0, e->d_counts[slot], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
+            CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
+        }
+        return 0;
+    };
+    rc = enqueue();
+    if (rc) {                                                      // DMA into the caller's buffers may be in flight: drain before reporting
+        const std::string msg = g_err;
+        host_sync(e);
+        g_err = msg;
+        return rc;
+    }
+    CK(cudaEventRecord(e->ev_busy, e->s_comp));                    // later device-entry calls wait for the pipeline's last pass
+    e->busy_recorded = true;
+    return sync ? host_sync(e) : 0;
 }
 
 extern "C" int ayq_forward_host(ayq_handle e, const float* img_host, int n, float* dets_host, int32_t* counts_host) {
-    return forward_host_impl(e, img_host, false, n, dets_host, counts_host);
+    return forward_host_impl(e, img_host, false, n, dets_host, counts_host, true);
 }
 extern "C" int ayq_forward_host_u8(ayq_handle e, const uint8_t* img_host, int n, float* dets_host, int32_t* counts_host) {
-    return forward_host_impl(e, img_host, true, n, dets_host, counts_host);
+    return forward_host_impl(e, img_host, true, n, dets_host, counts_host, true);
+}
+extern "C" int ayq_forward_host_async(ayq_handle e, const void* img_host, int is_u8, int n, float* dets_host, int32_t* counts_host) {
+    return forward_host_impl(e, img_host, is_u8 != 0, n, dets_host, counts_host, false);
+}
+extern "C" int ayq_wait(ayq_handle e) {
+    if (!e) return fail(-22, "ayq_wait: null handle");
+    CK(cudaSetDevice(e->device));
+    return host_sync(e);
 }
 
 // ---- taps ---------------------------------------------------------------------------------------------
@@ -746,15 +917,19 @@ extern "C" int ayq_export_buffer(ayq_handle e, int buf, int n, int32_t* dst, voi
     if (!e || buf < 0 || buf >= (int)e->bufs.size() || !dst) return fail(-22, "ayq_export_buffer: bad arguments");
     if (n != e->last_n) return fail(-22, "ayq_export_buffer: n=%d but the last pass had %d images", n, e->last_n);
     const BufDesc& b = e->bufs[buf];
+    int rc = wait_busy(e, (cudaStream_t)stream);
+    if (rc) return rc;
     export_planes_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(e->ws + e->buf_off[buf], b.elem_bytes, b.nplanes, n, b.H, b.W, dst);
     CK(cudaGetLastError());
-    return 0;
+    return mark_busy(e, (cudaStream_t)stream);
 }
 extern "C" int ayq_export_acc_tap(ayq_handle e, int tap, int n, int32_t* dst, void* stream) {
     if (!e || tap < 0 || tap >= (int)e->acc_taps.size() || !dst) return fail(-22, "ayq_export_acc_tap: bad tap %d (plan compiled without taps?)", tap);
     if (n != e->last_n) return fail(-22, "ayq_export_acc_tap: n=%d but the last pass had %d images", n, e->last_n);
+    int rc = wait_busy(e, (cudaStream_t)stream);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(dst, e->acc_taps[tap], e->acc_tap_elems[tap] * n * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return 0;
+    return mark_busy(e, (cudaStream_t)stream);
 }
 
 // ---- unit-level layer library -------------------------------------------------------------------------
@@ -859,6 +1034,8 @@ extern "C" int ayq_nms(ayq_handle e, const float* dbox_cls, int n, float* dets, 
     int rc = ensure_workspace(e, n < mb ? n : mb);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    rc = wait_busy(e, st);
+    if (rc) return rc;
     for (int i0 = 0; i0 < n; i0 += e->cap) {
         const int m = (n - i0) < e->cap ? (n - i0) : e->cap;
         float4* dbox = (float4*)(e->ws + e->off_dbox);
@@ -871,7 +1048,7 @@ extern "C" int ayq_nms(ayq_handle e, const float* dbox_cls, int n, float* dets, 
         nms_kernel<<<m, NMS_THREADS, NMS_SMEM, st>>>(a);
     }
     CK(cudaGetLastError());
-    return 0;
+    return mark_busy(e, st);
 }
 
 extern "C" int ayq_coord_float(ayq_handle e, const float* dbox_cls, int n, float* dets, int32_t* counts, void* stream) {
@@ -883,6 +1060,8 @@ extern "C" int ayq_coord_float(ayq_handle e, const float* dbox_cls, int n, float
     int rc = ensure_workspace(e, n < mb ? n : mb);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    rc = wait_busy(e, st);
+    if (rc) return rc;
     for (int i0 = 0; i0 < n; i0 += e->cap) {
         const int m = (n - i0) < e->cap ? (n - i0) : e->cap;
         float4* dbox = (float4*)(e->ws + e->off_dbox);
@@ -895,14 +1074,13 @@ extern "C" int ayq_coord_float(ayq_handle e, const float* dbox_cls, int n, float
         nms_float_kernel<<<m, NMS_THREADS, nmsf_smem_bytes(A), st>>>(a);
     }
     CK(cudaGetLastError());
-    return 0;
+    return mark_busy(e, st);
 }
 
 extern "C" int ayq_nms_boxes(const float* boxes, const float* scores, int nb, float* keep, int32_t* count, void* stream) {
     if (!boxes || !scores || !keep || !count || nb < 0 || nb > NMS_SORT_N) return fail(-22, "ayq_nms_boxes: 0 <= nb <= %d", NMS_SORT_N);
     if (nb == 0) { CK(cudaMemsetAsync(count, 0, sizeof(int), (cudaStream_t)stream)); return 0; }
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM)); attr_set = true; }
+    CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));   // per device: set on the current one
     NmsArgs a;
     a.dbox = nullptr; a.conf = nullptr; a.cls_id = nullptr; a.boxes = boxes; a.scores = scores;
     a.n = 1; a.A = nb; a.mode = 1; a.max_keep = NMS_TOPK; a.dets = keep; a.counts = count;

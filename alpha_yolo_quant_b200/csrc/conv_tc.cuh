@@ -512,6 +512,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
     }
 }
 
+#ifdef AYQ_TEST_BUILD   // cp.async-fed tcgen05 convolution: second implementation for the parity tests, not in the product library
 // dynamic smem: [A ring NS*KS*2048][B: resident nkc_pad*N*16 | ring NS*KS*N*16][tab 4N f32][bias N i32][lut 256 f32]
 // NBC > 0: cout = 16 * NBC known at compile time (channel loop unrolled, coefficients from `et`); NBC == 0: any cout,
 // coefficients from shared memory.
@@ -729,8 +730,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
 }
 
+#endif  // AYQ_TEST_BUILD
+
 }  // namespace tc
 
+#ifdef AYQ_TEST_BUILD
 typedef void (*TcKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::GroupTab);
 // instantiations: SiLU for every cout; requant8 / requant16 only for the Detect-head output convs (cout 64 / 80)
 static inline TcKernel tc_pick(int N, int epi) {
@@ -750,13 +754,17 @@ static inline TcKernel tc_pick(int N, int epi) {
     return nullptr;
 }
 
+#endif  // AYQ_TEST_BUILD
+
 static inline void tc_init(TcState& s) {
+#ifdef AYQ_TEST_BUILD
     const int ns[] = {16, 32, 48, 64, 80, 128};
     for (int epi = 0; epi < 3; ++epi)
         for (int N : ns) {
             TcKernel k = tc_pick(N, epi);
             if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         }
+#endif
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -767,6 +775,7 @@ static inline void tc_release(TcState&) {}
 // returns 0 = launched, 1 = shape not covered (caller uses the CUDA-core kernel), <0 = error
 static inline unsigned tc_magic(int d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)d - 1) / (unsigned)d); }
 
+#ifdef AYQ_TEST_BUILD
 // h_kc: the op's K-chunk list on the host (buffer byte offset, plane, dy, dx relative to the padded origin)
 static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const KChunk* h_kc, const float* h_tab /*[4][cout]*/, const int* h_bias, cudaStream_t st) {
     if (!s.ready) return 1;
@@ -834,5 +843,7 @@ static inline int tc_launch_conv(TcState& s, const ConvArgs& a, const KChunk* h_
     }
     return launch_k(kern, dim3(grid), dim3(tc::TC_THREADS), smem, st, a, tp, et, gt) == cudaSuccess ? 0 : -1;
 }
+
+#endif  // AYQ_TEST_BUILD
 
 }  // namespace ayq

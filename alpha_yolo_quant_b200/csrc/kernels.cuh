@@ -129,8 +129,10 @@ __device__ __forceinline__ void epilogue16(const ConvArgs& a, const int* acc, in
     }
 }
 
-// ---- generic dp4a convolution -------------------------------------------------------------------------
+// ---- generic dp4a convolution (TEST BUILD ONLY: an independent CUDA-core implementation the parity tests cross-check against;
+// the product library contains the TMA-fed tcgen05 convolution only) --------------------------------------
 // grid (ceil(n*Hout*Wout / 128), cout / NC), block 128: one output pixel x NC output channels per thread.
+#ifdef AYQ_TEST_BUILD
 template <int NC>
 __global__ void __launch_bounds__(128) conv_dp4a_kernel(const ConvArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(128) conv_dp4a_kernel(const ConvArgs a) {
 #pragma unroll
     for (int g = 0; g < NC / 16; ++g) epilogue16(a, acc + 16 * g, c0 + 16 * g, img, oy, ox, lut_s);
 }
+#endif  // AYQ_TEST_BUILD
 
 // ---- Conv_P1 + quant_matrix ---------------------------------------------------------------------------
 struct P1Args {
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(256) conv_p1_kernel(const __grid_constant__ P1
 //     (no bank conflicts);
 //   * the accumulators start at bias + 0x4B400000 and go straight into silu_magic (no I2F, no lower clamp).
 // Geometry: H = 2 Hout, W = 2 Wout, Wout % 32 == 0, Hout % 8 == 0 (checked by the host).  pc.i1 holds -k1p * C.
+#ifdef AYQ_TEST_BUILD   // CUDA-core lean Conv_P1: cross-check implementation of conv_p1_tc_kernel, test build only
 template <bool U8>
 __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc) {
     __shared__ __align__(16) unsigned sE[2 * P1_TH + 1][P1_TW + 2];    // [r][j]     input x = 2 x0 + 2 j
@@ -380,6 +384,7 @@ __global__ void __launch_bounds__(256) conv_p1_fast_kernel(const __grid_constant
                                                    pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
     }
 }
+#endif  // AYQ_TEST_BUILD
 
 // ---- per-image abs-max --------------------------------------------------------------------------------
 // grid (blocks, n); out[] must be zeroed first.  |x| >= 0 so the float bit pattern orders like an int.

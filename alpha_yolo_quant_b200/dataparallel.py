@@ -78,3 +78,91 @@ def bind_to_gpu_numa_node(device_index):
     except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):
         return None
 
+
+
+class DataParallelYolo:
+    """N host images in, N results out, over every GPU of the box (north_star: "the batch of images is sharded across the 8 GPUs
+    of one box ... each GPU loads its own copy of the weights and results are gathered to the host, with no NCCL needed on the
+    inner path").  Re-hosts the reference's validation loop body (stage_8_torch.py:1004-1013: img -> model(img) -> boxes,
+    classes on the host) for whole batches.  Two ways to drive it:
+
+      * one process, G GPUs (`devices=[0, 1, ...]`): one engine (= one weight copy + workspace) per device, the batch is cut into
+        contiguous shards of ceil(N / G) images, every shard is queued with ayq_forward_host_async on its GPU (the calls only
+        enqueue, so one host thread keeps all GPUs busy) and the results land directly in ONE pair of host arrays in image order;
+      * one process per GPU under torchrun (`group=`): `forward_shard` runs this rank's shard, `gather` (an all_gather of the
+        small result arrays, outside the data path) returns all N results in image order on rank 0.
+
+    `engine_factory(plan, device, max_batch)` exists for the CPU tests (a stub engine); the default builds the CUDA engine and
+    fails loudly without one.
+    """
+
+    def __init__(self, plan, devices=None, max_batch=256, group=None, engine_factory=None):
+        if engine_factory is None:
+            from . import engine as _eng
+            engine_factory = _eng.Engine
+        self.group = group
+        if group is not None or (devices is None and dist.is_available() and dist.is_initialized()):
+            # one rank per GPU: this process owns the GPU torch has selected for it
+            dev = torch.cuda.current_device() if devices is None else devices[0]
+            self.devices = [dev]
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            if devices is None:
+                devices = list(range(torch.cuda.device_count()))
+            if not devices:
+                raise RuntimeError('DataParallelYolo: no CUDA device (there is no CPU path)')
+            self.devices = list(devices)
+            self.rank, self.world = 0, 1
+        self.engines = [engine_factory(plan, d, max_batch) for d in self.devices]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    # ---- one process, G GPUs
+    def forward_host(self, images, dets=None, counts=None):
+        """images: host tensor (N,3,640,640), uint8 (the loader's format before ToTensor, stage_8_torch.py:985-990) or float32 in
+        [0,1]; pinned for full speed.  Returns (dets (N,300,6) float32, counts (N) int32) host tensors (pinned) whose row i is
+        the reference's model(images[i:i+1]) (counts[i] == 0 <=> (None, None))."""
+        n = images.shape[0]
+        if dets is None:
+            dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32)
+            counts = torch.empty((n,), dtype=torch.int32)
+            if torch.cuda.is_available():
+                dets, counts = dets.pin_memory(), counts.pin_memory()
+        g = len(self.engines)
+        busy = []
+        for r, e in enumerate(self.engines):
+            lo, hi = shard_range(n, g, r)
+            if hi > lo:
+                e.forward_host_async(images[lo:hi], dets[lo:hi], counts[lo:hi])     # contiguous slices of contiguous tensors
+                busy.append(e)
+        for e in busy:
+            e.wait()
+        return dets, counts
+
+    # ---- one process per GPU (torchrun): this rank's shard of a global batch of n_images
+    def forward_shard(self, shard_images, dets=None, counts=None):
+        """Runs THIS rank's contiguous shard (host tensor, shard_range(n_images, world, rank) of the global batch) on its GPU
+        through the pipelined host entry; returns pinned host (dets, counts) of the shard."""
+        m = shard_images.shape[0]
+        if dets is None:
+            dets = torch.empty((m, MAX_DET, DET_STRIDE), dtype=torch.float32)
+            counts = torch.empty((m,), dtype=torch.int32)
+            if torch.cuda.is_available():
+                dets, counts = dets.pin_memory(), counts.pin_memory()
+        if m:
+            self.engines[0].forward_host_async(shard_images, dets, counts)
+            self.engines[0].wait()
+        return dets, counts
+
+    def gather(self, dets, counts, n_images, dst=0):
+        """All ranks' shard results -> (N,300,6), (N) in image order on rank dst (None, None elsewhere)."""
+        if self.world == 1:
+            return dets, counts
+        if dist.get_backend(self.group) == 'nccl':
+            dev = torch.device('cuda', self.devices[0])
+            d, c = gather_detections(dets.to(dev), counts.to(dev), n_images, self.group, dst)
+            return (d.cpu(), c.cpu()) if d is not None else (None, None)
+        return gather_detections(dets, counts, n_images, self.group, dst)

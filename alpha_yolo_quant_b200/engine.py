@@ -13,6 +13,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 # AYQ_ROLE_PROF=1 (role-level cycle counters of the conv kernel) needs the profiling build of the same sources
 LIB_PATH = os.environ.get('AYQ_LIB') or os.path.join(HERE, 'libayq_prof.so' if os.environ.get('AYQ_ROLE_PROF') else 'libayq.so')
+# Test build: the product sources + the two cross-check convolution families (dp4a, cp.async-fed tcgen05).  Only tests load it.
+TEST_LIB_PATH = os.path.join(HERE, 'libayq_test.so')
 MAX_DET, DET_STRIDE, ANCHORS = 300, 6, 8400
 
 _c = ctypes
@@ -28,6 +30,9 @@ SIGNATURES = {
     'ayq_forward': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp]),
     'ayq_forward_host': (_int, [_vp, _vp, _int, _vp, _vp]),
     'ayq_forward_host_u8': (_int, [_vp, _vp, _int, _vp, _vp]),
+    'ayq_forward_host_async': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
+    'ayq_wait': (_int, [_vp]),
+    'ayq_get_conv_impls': (_int, [_vp, _vp, _int]),
     'ayq_export_buffer': (_int, [_vp, _int, _int, _vp, _vp]),
     'ayq_buffer_shape': (_int, [_vp, _int, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_int)]),
     'ayq_export_acc_tap': (_int, [_vp, _int, _int, _vp, _vp]),
@@ -50,19 +55,19 @@ SIGNATURES = {
     'ayq_quant_weights_f32': (_int, [_vp, _vp, _int, _sz, _int, _c.c_double, _vp, _vp, _vp, _vp]),
 }
 
-_LIB = None
+_LIBS = {}
 
 
 class AyqError(RuntimeError):
     pass
 
 
-def load_library(path=LIB_PATH):
-    """dlopen libayq.so and bind every entry point.  Raises if the library is missing (build it with
+def load_library(path=None):
+    """dlopen libayq.so (or the library at `path`) and bind every entry point.  Raises if the library is missing (build it with
     `python -m alpha_yolo_quant_b200.build`); never falls back to anything else."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
+    path = os.path.abspath(path or LIB_PATH)
+    if path in _LIBS:
+        return _LIBS[path]
     if not os.path.exists(path):
         raise AyqError(f'{path} not found: build the CUDA extension first (python -m alpha_yolo_quant_b200.build). '
                        'There is no CPU fallback.')
@@ -71,13 +76,13 @@ def load_library(path=LIB_PATH):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _LIB = lib
+    _LIBS[path] = lib
     return lib
 
 
-def check(rc):
+def check(rc, lib=None):
     if rc < 0:
-        raise AyqError(f'libayq error {rc}: {load_library().ayq_last_error().decode()}')
+        raise AyqError(f'libayq error {rc}: {(lib or load_library()).ayq_last_error().decode()}')
     return rc
 
 
@@ -93,17 +98,20 @@ def _require_cuda(t, name):
 class Engine:
     """One handle per GPU (not thread-safe), created from a compiled plan (plan.compile_plan)."""
 
-    def __init__(self, plan, device=0, max_batch=256):
-        self.lib = load_library()
+    def __init__(self, plan, device=0, max_batch=256, lib_path=None):
+        self.lib = load_library(lib_path)
         if not torch.cuda.is_available():
             raise AyqError('Engine: no CUDA device available; the integer YOLOv8n path has no CPU fallback')
         self.plan = plan
         self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
         self._h = _vp()
         blob = plan.blob
-        check(self.lib.ayq_create(blob, len(blob), self.device.index, ctypes.byref(self._h)))
-        check(self.lib.ayq_set_max_batch(self._h, max_batch))
+        self._ck(self.lib.ayq_create(blob, len(blob), self.device.index, ctypes.byref(self._h)))
+        self._ck(self.lib.ayq_set_max_batch(self._h, max_batch))
         self.max_batch = max_batch
+
+    def _ck(self, rc):
+        return check(rc, self.lib)
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
@@ -128,13 +136,13 @@ class Engine:
             dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=self.device)
             counts = torch.empty((n,), dtype=torch.int32, device=self.device)
             dbc = torch.empty((n, 84, ANCHORS), dtype=torch.float32, device=self.device) if want_dbox_cls else None
-            check(self.lib.ayq_forward(self._h, img.data_ptr(), n, dbc.data_ptr() if dbc is not None else None,
+            self._ck(self.lib.ayq_forward(self._h, img.data_ptr(), n, dbc.data_ptr() if dbc is not None else None,
                                        dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
         return (dets, counts, dbc) if want_dbox_cls else (dets, counts)
 
     def forward_into(self, img, dets, counts):
         """Allocation-free variant for timing loops."""
-        check(self.lib.ayq_forward(self._h, img.data_ptr(), img.shape[0], None, dets.data_ptr(), counts.data_ptr(),
+        self._ck(self.lib.ayq_forward(self._h, img.data_ptr(), img.shape[0], None, dets.data_ptr(), counts.data_ptr(),
                                    _stream_ptr(self.device)))
 
     def forward_host(self, img_host, dets_host=None, counts_host=None):
@@ -149,8 +157,35 @@ class Engine:
         fn = {torch.float32: self.lib.ayq_forward_host, torch.uint8: self.lib.ayq_forward_host_u8}.get(img_host.dtype)
         if fn is None:
             raise AyqError(f'forward_host: float32 or uint8 images, got {img_host.dtype}')
-        check(fn(self._h, img_host.data_ptr(), n, dets_host.data_ptr(), counts_host.data_ptr()))
+        self._ck(fn(self._h, img_host.data_ptr(), n, dets_host.data_ptr(), counts_host.data_ptr()))
         return dets_host, counts_host
+
+    def forward_host_async(self, img_host, dets_host, counts_host):
+        """Enqueue forward_host without waiting (ayq_forward_host_async); the three host tensors must stay alive and untouched
+        until wait().  Several calls may be queued (each with its own buffers): the upload of one overlaps the kernels of the
+        previous one."""
+        if img_host.is_cuda or dets_host.is_cuda or counts_host.is_cuda:
+            raise AyqError('forward_host_async takes host tensors')
+        if not img_host.is_contiguous():
+            raise AyqError('forward_host_async: contiguous host images required (the copy is asynchronous)')
+        if img_host.dtype not in (torch.float32, torch.uint8):
+            raise AyqError(f'forward_host_async: float32 or uint8 images, got {img_host.dtype}')
+        n = img_host.shape[0]
+        if tuple(dets_host.shape) != (n, MAX_DET, DET_STRIDE) or dets_host.dtype != torch.float32 or counts_host.dtype != torch.int32 or counts_host.numel() != n:
+            raise AyqError('forward_host_async: dets_host float32 (n,300,6) and counts_host int32 (n) required')
+        self._ck(self.lib.ayq_forward_host_async(self._h, img_host.data_ptr(), 1 if img_host.dtype == torch.uint8 else 0, n,
+                                                 dets_host.data_ptr(), counts_host.data_ptr()))
+
+    def wait(self):
+        """Block until every queued forward_host_async call has delivered its results."""
+        self._ck(self.lib.ayq_wait(self._h))
+
+    def conv_impls(self):
+        """Per plan op: 2 / 1 / 0 = the conv kernel family that ran it in the last pass (2 = TMA-fed tcgen05), -2 = not a conv."""
+        n = self.plan.n_ops
+        out = np.zeros(n, np.int32)
+        self._ck(self.lib.ayq_get_conv_impls(self._h, out.ctypes.data, n))
+        return out
 
     def nms(self, dbox_cls):
         _require_cuda(dbox_cls, 'Engine.nms')
@@ -159,7 +194,7 @@ class Engine:
         assert tuple(dbox_cls.shape[1:]) == (84, ANCHORS)
         dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=dbox_cls.device)
         counts = torch.empty((n,), dtype=torch.int32, device=dbox_cls.device)
-        check(self.lib.ayq_nms(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
+        self._ck(self.lib.ayq_nms(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
         return dets, counts
 
     def coord_float(self, dbox_cls):
@@ -170,19 +205,19 @@ class Engine:
         assert tuple(dbox_cls.shape[1:]) == (84, ANCHORS)
         dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=dbox_cls.device)
         counts = torch.empty((n,), dtype=torch.int32, device=dbox_cls.device)
-        check(self.lib.ayq_coord_float(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
+        self._ck(self.lib.ayq_coord_float(self._h, dbox_cls.data_ptr(), n, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
         return dets, counts
 
     # -- taps / introspection
     def buffer_shape(self, buf):
         c, h, w = _int(), _int(), _int()
-        check(self.lib.ayq_buffer_shape(self._h, buf, ctypes.byref(c), ctypes.byref(h), ctypes.byref(w)))
+        self._ck(self.lib.ayq_buffer_shape(self._h, buf, ctypes.byref(c), ctypes.byref(h), ctypes.byref(w)))
         return c.value, h.value, w.value
 
     def export_buffer(self, buf, n):
         c, h, w = self.buffer_shape(buf)
         out = torch.empty((n, c, h, w), dtype=torch.int32, device=self.device)
-        check(self.lib.ayq_export_buffer(self._h, buf, n, out.data_ptr(), _stream_ptr(self.device)))
+        self._ck(self.lib.ayq_export_buffer(self._h, buf, n, out.data_ptr(), _stream_ptr(self.device)))
         if buf in self.plan.info.get('ps_bufs', ()):
             # phase-split buffer [(y&1)*2 + (x&1)][plane][n][h][w][16] -> (n, C, 2h, 2w)
             out = out.view(n, 2, 2, c // 4, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c // 4, 2 * h, 2 * w).contiguous()
@@ -191,29 +226,29 @@ class Engine:
     def export_acc_tap(self, tap, n):
         name, c, h, w = self.plan.info['acc_taps'][tap]
         out = torch.empty((n, c, h, w), dtype=torch.int32, device=self.device)
-        check(self.lib.ayq_export_acc_tap(self._h, tap, n, out.data_ptr(), _stream_ptr(self.device)))
+        self._ck(self.lib.ayq_export_acc_tap(self._h, tap, n, out.data_ptr(), _stream_ptr(self.device)))
         return out
 
     def set_conv_impl(self, impl):
-        check(self.lib.ayq_set_conv_impl(self._h, {'dp4a': 0, 'tcgen05': 1, 'tma': 2}.get(impl, impl)))
+        self._ck(self.lib.ayq_set_conv_impl(self._h, {'dp4a': 0, 'tcgen05': 1, 'tma': 2}.get(impl, impl)))
 
     def set_max_batch(self, mb):
-        check(self.lib.ayq_set_max_batch(self._h, mb))
+        self._ck(self.lib.ayq_set_max_batch(self._h, mb))
         self.max_batch = mb
 
     def set_profiling(self, on):
-        check(self.lib.ayq_set_profiling(self._h, 1 if on else 0))
+        self._ck(self.lib.ayq_set_profiling(self._h, 1 if on else 0))
 
     def op_times(self):
         n = self.plan.n_ops + 1
         ms = np.zeros(n, np.float32)
         calls = np.zeros(n, np.int32)
-        check(self.lib.ayq_get_op_times(self._h, ms.ctypes.data, calls.ctypes.data, n))
+        self._ck(self.lib.ayq_get_op_times(self._h, ms.ctypes.data, calls.ctypes.data, n))
         return ms, calls
 
     @property
     def launches_per_pass(self):
-        return check(self.lib.ayq_launches_per_pass(self._h))
+        return self._ck(self.lib.ayq_launches_per_pass(self._h))
 
     @property
     def workspace_bytes(self):

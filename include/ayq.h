@@ -9,8 +9,14 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a
  * negative errno-style code, ayq_last_error() gives the message of the last failure on the
  * calling thread; image / detection buffers are caller-owned (torch allocations), the engine owns
- * its packed weights, tables and activation workspace; all launches go to the caller's stream
- * (a cudaStream_t passed as void*); a handle is bound to one GPU and is not thread-safe.
+ * its packed weights, tables and activation workspace; a handle is bound to one GPU and is not thread-safe.
+ *
+ * Stream semantics.  Entry points that take a `stream` (a cudaStream_t passed as void*) launch all their kernels on it and
+ * return without synchronising.  The host-buffer entries (ayq_forward_host*, ayq_forward_host_async) run on three internal
+ * non-blocking streams (H2D | kernels | D2H).  Every entry shares the ONE engine-owned workspace, so the engine orders them
+ * itself: each entry first makes its stream(s) wait for an event recorded at the end of the previous entry (whatever stream
+ * that one ran on) and records the event again when it has enqueued its own work.  Calls on different streams are therefore
+ * serialised on the device in call order and never overlap; the caller only has to order accesses to its OWN buffers.
  */
 #ifndef AYQ_H
 #define AYQ_H
@@ -57,6 +63,14 @@ int ayq_forward(ayq_handle h, const float* img, int n, float* dbox_cls, float* d
 int ayq_forward_host(ayq_handle h, const float* img_host, int n, float* dets_host, int32_t* counts_host);
 /* Same, images given as uint8 (n,3,640,640) CHW: ToTensor (u8 / 255, stage_8_torch.py:985-990) runs on the GPU. */
 int ayq_forward_host_u8(ayq_handle h, const uint8_t* img_host, int n, float* dets_host, int32_t* counts_host);
+/* Asynchronous form of the two calls above (the validation loop of stage_8_torch.py:1004-1013 with the next batch's upload
+ * overlapping the current batch's kernels): enqueues the whole call on the engine's internal streams and returns at once;
+ * img_host (float32 when is_u8 == 0, uint8 otherwise), dets_host and counts_host must stay valid, and the results may only be
+ * read, after the next ayq_wait().  Any number of calls may be queued before a wait (each with its own host buffers); they
+ * run back to back, so only the first upload and the last pass of the whole sequence are exposed. */
+int ayq_forward_host_async(ayq_handle h, const void* img_host, int is_u8, int n, float* dets_host, int32_t* counts_host);
+/* blocks until every queued ayq_forward_host_async call has delivered its results; returns the first device error, if any */
+int ayq_wait(ayq_handle h);
 
 /* Per-layer taps for parity tests: copies activation buffer `buf` (plan.info['bufs']) of the last pass
  * into dst as int32 NCHW (n, 16*nplanes, H, W). */
@@ -66,8 +80,14 @@ int ayq_buffer_shape(ayq_handle h, int buf, int* channels, int* height, int* wid
 int ayq_export_acc_tap(ayq_handle h, int tap, int n, int32_t* dst, void* stream);
 /* number of kernels one internal pass launches (bench.py gpu_launches) */
 int ayq_launches_per_pass(ayq_handle h);
-/* select the convolution kernel family: 0 = CUDA-core dp4a kernel, 1 = tcgen05/TMEM kernel */
+/* Convolution kernel family: 2 = TMA-fed tcgen05 / TMEM implicit GEMM (conv_tma_kernel) -- the ONLY family in the product
+ * library libayq.so, where any other value returns an error and a conv shape the kernel does not cover is an error when the
+ * workspace is built (no fallback).  The test build libayq_test.so (same sources, -DAYQ_TEST_BUILD) additionally carries two
+ * independent implementations for cross-checking: 0 = CUDA-core dp4a kernel, 1 = tcgen05 kernel fed by cp.async. */
 int ayq_set_conv_impl(ayq_handle h, int impl);
+/* per conv op of the last pass, which implementation ran it (2 / 1 / 0 as above, -1 not run yet); returns the number of ops
+ * written (ops that are not convolutions get -2).  Parity tests assert that every conv ran on the TMA kernel. */
+int ayq_get_conv_impls(ayq_handle h, int32_t* impl, int cap);
 /* kernel time accounting: when enabled, every pass records CUDA events around each op;
  * ayq_get_op_times copies per-op accumulated milliseconds and launch counts (arrays of n_ops). */
 int ayq_set_profiling(ayq_handle h, int enabled);

@@ -100,3 +100,89 @@ def test_numa_binding_is_a_no_op_without_topology():
     assert r is None or set(r) <= before
     if r is None:
         assert os.sched_getaffinity(0) == before
+
+
+class _StubEngine:
+    """CPU stand-in with the Engine methods DataParallelYolo uses; 'detections' encode the image's first pixel and the device."""
+    log = []
+
+    def __init__(self, plan, device, max_batch):
+        self.device, self.queue = device, []
+
+    def forward_host_async(self, img, dets, counts):
+        assert img.is_contiguous() and dets.is_contiguous()
+        self.queue.append((img, dets, counts))
+        _StubEngine.log.append(('enqueue', self.device, img.shape[0]))
+
+    def wait(self):
+        _StubEngine.log.append(('wait', self.device))
+        for img, dets, counts in self.queue:
+            for i in range(img.shape[0]):
+                k = int(img[i, 0, 0, 0]) % 5
+                counts[i] = k
+                dets[i].zero_()
+                dets[i, :k, 0] = float(img[i, 0, 0, 0])
+                dets[i, :k, 5] = self.device
+        self.queue = []
+
+    def close(self):
+        pass
+
+
+def test_data_parallel_single_process_sharding_and_order():
+    """One process, G 'GPUs': contiguous ceil(N / G) shards, every shard queued before the first wait (so the devices overlap),
+    results in image order in one pair of arrays; ragged and empty shards."""
+    for n, g in ((10, 4), (8, 8), (3, 8), (257, 2), (1, 1)):
+        _StubEngine.log = []
+        dpy = dp.DataParallelYolo(plan=None, devices=list(range(g)), engine_factory=_StubEngine)
+        img = torch.zeros((n, 3, 2, 2), dtype=torch.uint8)
+        img[:, 0, 0, 0] = torch.arange(n, dtype=torch.uint8)
+        dets, counts = dpy.forward_host(img)
+        per = (n + g - 1) // g
+        for i in range(n):
+            k = (i % 256) % 5
+            assert int(counts[i]) == k
+            assert dets[i, :k, 0].tolist() == [float(i % 256)] * k and dets[i, :k, 5].tolist() == [float(i // per)] * k
+        kinds = [t[0] for t in _StubEngine.log]
+        assert kinds == sorted(kinds)                              # all 'enqueue' entries precede the first 'wait'
+        assert sum(t[2] for t in _StubEngine.log if t[0] == 'enqueue') == n
+        dpy.close()
+
+
+def _dp_worker(rank, world, port, n_images, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    dpy = dp.DataParallelYolo(plan=None, devices=[rank], group=dist.group.WORLD, engine_factory=_StubEngine)
+    img = torch.zeros((n_images, 3, 2, 2), dtype=torch.uint8)
+    img[:, 0, 0, 0] = torch.arange(n_images, dtype=torch.uint8)
+    lo, hi = dp.shard_range(n_images, world, rank)
+    d, c = dpy.forward_shard(img[lo:hi])
+    D, C = dpy.gather(d, c, n_images)
+    ok = True
+    if rank == 0:
+        per = (n_images + world - 1) // world
+        for i in range(n_images):
+            k = i % 5
+            ok = ok and int(C[i]) == k and D[i, :k, 0].tolist() == [float(i)] * k and D[i, :k, 5].tolist() == [float(i // per)] * k
+    else:
+        ok = D is None
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_one_process_per_gpu_world_size_2():
+    """torchrun layout on CPU (gloo): each rank runs its shard, rank 0 gets all N results in image order."""
+    ctx = mp.get_context('spawn')
+    for n_images in (7, 2, 1):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, n_images, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=120) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert res == [(0, True), (1, True)], (n_images, res)

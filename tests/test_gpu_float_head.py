@@ -28,7 +28,7 @@ def _setup(golden_dir, taps, impl='tma', max_batch=8):
     from alpha_yolo_quant_b200 import engine, loaders, plan
     K, sd, sc, ma = loaders.load_workload_npz(os.path.join(golden_dir, 'workload_k8.npz'))
     p = plan.compile_plan(sd, sc, ma, K, sigmoid_range=7, taps=taps, head='float')
-    e = engine.Engine(p, 0, max_batch)
+    e = engine.Engine(p, 0, max_batch, lib_path=None if impl == 'tma' else engine.TEST_LIB_PATH)   # cross-check families: test build only
     e.set_conv_impl(impl)
     return p, e
 

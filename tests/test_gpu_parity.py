@@ -24,13 +24,22 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
 
-def _setup(golden_dir, k, taps, impl='dp4a', max_batch=64):
+def _setup(golden_dir, k, taps, impl='tma', max_batch=64):
+    """impl 'tma' = the product library (libayq.so: TMA-fed tcgen05 convolution only).  'dp4a' / 'tcgen05' = the two independent
+    cross-check implementations, which exist only in the test build (libayq_test.so)."""
     from alpha_yolo_quant_b200 import engine, loaders, plan
     K, sd, sc, ma = loaders.load_workload_npz(os.path.join(golden_dir, f'workload_k{k}.npz'))
     p = plan.compile_plan(sd, sc, ma, K, taps=taps)
-    e = engine.Engine(p, 0, max_batch)
+    e = engine.Engine(p, 0, max_batch, lib_path=None if impl == 'tma' else engine.TEST_LIB_PATH)
     e.set_conv_impl(impl)
     return p, e
+
+
+def _assert_all_convs_on_tma(p, e):
+    """No silent fallback: every convolution of the last pass ran on conv_tma_kernel (ayq_get_conv_impls)."""
+    impls = e.conv_impls()
+    conv = impls[impls != -2]
+    assert conv.size == 62 and (conv == 2).all(), impls.tolist()
 
 
 def _images(seeds):
@@ -51,6 +60,8 @@ def test_every_tensor_matches_reference_goldens(golden_dir, k, impl):
     x = _images(range(n)).cuda()
     dets, counts, dbc = e.forward(x, want_dbox_cls=True)
     torch.cuda.synchronize()
+    if impl == 'tma':
+        _assert_all_convs_on_tma(p, e)                             # K = 8 / 6 / 4, plan with accumulator taps
     from alpha_yolo_quant_b200 import plan as P
     bad = []
     acc = [e.export_acc_tap(t, n).cpu().numpy() for t in range(p.n_acc_taps)]
@@ -92,6 +103,8 @@ def test_all_golden_detections(golden_dir, impl):
     p, e = _setup(golden_dir, 8, taps=False, impl=impl)
     n = int(g['n_images'])
     dets, counts = e.forward(_images(range(n)).cuda())
+    if impl == 'tma':
+        _assert_all_convs_on_tma(p, e)                             # production plan (MAGIC epilogues, phase-split stores)
     seen = set()
     for i in range(n):
         pre = f'img{i}_'
@@ -137,13 +150,50 @@ def test_host_entry_points(golden_dir):
     seeds = [0, 1, 2, 5, 6]
     u8 = torch.from_numpy(np.stack([synth.synth_image_u8(s) for s in seeds]))
     xs = _images(seeds)
-    dets, counts = e.forward(xs.cuda())
-    dh, ch = e.forward_host(xs.pin_memory())
+    dets, counts = e.forward(xs.cuda())                          # asynchronous on torch's stream; the host entries run on the
+    dh, ch = e.forward_host(xs.pin_memory())                     # engine's own streams: the engine orders them (ev_busy), no sync here
     du, cu = e.forward_host(u8.pin_memory())
+    torch.cuda.synchronize()
     assert torch.equal(ch, counts.cpu()) and torch.equal(cu, counts.cpu())
     for i in range(len(seeds)):
         k = int(ch[i])
         assert torch.equal(dh[i, :k], dets[i, :k].cpu()) and torch.equal(du[i, :k], dets[i, :k].cpu())
+    # asynchronous form: three calls queued behind one another (own buffers each), one wait
+    outs = []
+    for src in (u8, xs, u8[[4, 0, 3]].contiguous()):
+        src = src.pin_memory()
+        d = torch.empty((src.shape[0], 300, 6)).pin_memory()
+        c = torch.empty((src.shape[0],), dtype=torch.int32).pin_memory()
+        e.forward_host_async(src, d, c)
+        outs.append((src, d, c))
+    d2, c2 = e.forward(xs.cuda())                                # a device entry queued behind the asynchronous host calls
+    e.wait()
+    torch.cuda.synchronize()
+    assert torch.equal(c2, counts)
+    for (src, d, c), order in zip(outs, ([0, 1, 2, 3, 4], [0, 1, 2, 3, 4], [4, 0, 3])):
+        for j, i in enumerate(order):
+            k = int(counts[i])
+            assert int(c[j]) == k and torch.equal(d[j, :k], dets[i, :k].cpu()), (order, j)
+    e.close()
+
+
+def test_entries_on_different_streams_are_ordered_by_the_engine(golden_dir):
+    """Two ayq_forward calls on two different streams share the engine's workspace: the engine serialises them (include/ayq.h,
+    stream semantics), so both results must be right without any caller-side synchronisation between the calls."""
+    p, e = _setup(golden_dir, 8, taps=False, max_batch=8)
+    xa, xb = _images([1, 2, 5, 9]).cuda(), _images([3, 10, 0, 6]).cuda()
+    ra = e.forward(xa); rb = e.forward(xb)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            da, ca = e.forward(xa)
+        with torch.cuda.stream(s2):
+            db, cb = e.forward(xb)
+    torch.cuda.synchronize()
+    assert torch.equal(ca, ra[1]) and torch.equal(cb, rb[1])
+    for i in range(4):
+        assert torch.equal(da[i, :int(ca[i])], ra[0][i, :int(ca[i])]) and torch.equal(db[i, :int(cb[i])], rb[0][i, :int(cb[i])])
     e.close()
 
 

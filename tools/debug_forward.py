@@ -17,13 +17,13 @@ from tests.test_gpu_parity import REQUANT_ORDER  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--k', type=int, default=8)
-    ap.add_argument('--impl', default='dp4a')
+    ap.add_argument('--impl', default='tma')
     ap.add_argument('--n', type=int, default=2)
     a = ap.parse_args()
     wpath = os.path.join(REPO, 'tests', 'golden', f'workload_k{a.k}.npz')
     K, sd, sc, ma = loaders.load_workload_npz(wpath)
     p = plan.compile_plan(sd, sc, ma, K, taps=True)
-    e = engine.Engine(p, 0, 8)
+    e = engine.Engine(p, 0, 8, lib_path=None if a.impl == 'tma' else engine.TEST_LIB_PATH)
     e.set_conv_impl(a.impl)
     x = synth.to_input_array([synth.synth_image_u8(s) for s in range(a.n)])
     o = Y.OracleYolov8(Y.Workload(wpath))
