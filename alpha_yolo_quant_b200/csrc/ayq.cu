@@ -82,6 +82,8 @@ struct ayq_engine {
     std::vector<int> host_tail;            // AYQ_HOST_TAIL=a,b,..: sizes the last pass of a host call is split into (sum = pass size)
     int host_pass = 0, host_ramp = 0;      // AYQ_HOST_PASS: pass size of the host pipeline (default 64); AYQ_HOST_RAMP=1: smaller passes at both ends
     int p1_chunk = 0;                      // AYQ_P1_CHUNK: images per abs-max -> Conv_P1 chunk (fp32 device input), 0 = whole pass
+    bool p1_fuse = false;                  // AYQ_P1_FUSE=1: abs-max inside Conv_P1 (one HBM read of the image; measured slower, off)
+    bool last_fused = false;               // the last pass ran the fused abs-max + Conv_P1 kernel (one launch fewer)
     bool p1_dp4a = false;                  // AYQ_P1_DP4A=1: keep Conv_P1 on the CUDA cores (conv_p1_fast_kernel) also when a tcgen05 conv family is selected
     bool role_prof = false;                // AYQ_ROLE_PROF=1: per-op warp-role cycle counters (conv_tma only), dumped at destroy
     long long* d_role = nullptr;
@@ -142,7 +144,7 @@ static int ensure_workspace_impl(ayq_engine* e, int n) {
         off = align_up(off + (size_t)b.nplanes * cap * b.H * b.W * 16 * b.elem_bytes, 1024);
     }
     const int A = e->hdr.n_anchors;
-    e->off_amax = off; off = align_up(off + sizeof(float) * cap, 1024);
+    e->off_amax = off; off = align_up(off + sizeof(float) * cap + sizeof(unsigned) * (cap + 1), 1024);   // amax[cap] | fused Conv_P1: ticket, band counters[cap]
     e->off_dbox = off; off = align_up(off + sizeof(float4) * (size_t)cap * A, 1024);
     e->off_conf = off; off = align_up(off + sizeof(int) * (size_t)cap * A, 1024);
     e->off_cls = off;  off = align_up(off + sizeof(int) * (size_t)cap * A, 1024);
@@ -304,6 +306,10 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 #endif
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
     CK(cudaFuncSetAttribute(nms_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nmsf_smem_bytes(h.n_anchors)));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
@@ -312,6 +318,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     if (e->role_prof) { return fail(-22, "AYQ_ROLE_PROF=1 needs the profiling build of the library (libayq_prof.so: python -m alpha_yolo_quant_b200.build --prof)"); }
 #endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
+    e->p1_fuse = getenv("AYQ_P1_FUSE") != nullptr;           // off: measured slower than the two kernels (843 vs 184 + 439 us per 256 images)
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_PASS")) e->host_pass = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_RAMP")) e->host_ramp = atoi(ev);
@@ -436,7 +443,7 @@ extern "C" int ayq_get_conv_impls(ayq_handle e, int32_t* impl, int cap) {
 }
 extern "C" int ayq_launches_per_pass(ayq_handle e) {
     if (!e) return fail(-22, "null handle");
-    return (int)e->ops.size() + 1;          // + the abs-max reduction; the memset node is not a kernel
+    return (int)e->ops.size() + (e->last_fused ? 0 : 1);   // + the abs-max reduction unless it is fused into Conv_P1; the memset node is not a kernel
 }
 
 // ---- one pass over n <= cap images ---------------------------------------------------------------------
@@ -474,8 +481,14 @@ static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {
     TmaLaunch& L = e->tma_cache[opi];
     const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
     const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
-    if (L.n != n) tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
-                              (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
+    if (L.n != n) {
+        tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
+                    (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
+        if (getenv("AYQ_PLAN_DUMP"))
+            fprintf(stderr, "plan %-20s n=%d ok=%d cout=%3d %3dx%-3d s%d nkc=%3d | %s fast=%d gen=%d resB=%d NS=%2d slot=%5dB nbuf=%d tiles=%d smem=%zuK grid=%u\n",
+                    (const char*)(e->host_data.data() + f[CF_NAME_OFF]), n, L.ok, a.cout, a.Hout, a.Wout, a.stride, a.nkc,
+                    L.pl.halo ? "halo " : "boxes", L.fast, L.gen_outs, L.tp.resident_b, L.tp.NS, L.pl.a_slot_bytes, L.tp.nbuf, L.tp.ntiles, L.smem / 1024, L.grid);
+    }
     return L.ok;
 }
 static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
@@ -514,7 +527,23 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
 #endif
 }
 
-struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; };
+struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; bool p1_fused = false; };
+
+// Conv_P1 takes the lean tensor-core kernel (conv_p1_tc_kernel, MAGIC epilogue) when K = 8, no accumulator tap is asked for, the
+// geometry is the 640 -> 320 one it is written for and the host can prove the epilogue's range conditions from the plan.
+static bool p1_lean(ayq_engine* e, const int32_t* f, const PassArgs& pa) {
+    const int H = e->hdr.img_h, W = e->hdr.img_w, n = pa.n;
+    const int Hout = f[P1_HOUT], Wout = f[P1_WOUT], M = f[P1_CLAMP];
+    const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);
+    const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);
+    const int* hb = (const int*)(e->host_data.data() + f[P1_BIAS_OFF]);
+    long long sw[16];
+    for (int co = 0; co < 16; ++co) { sw[co] = 0; for (int k = 0; k < 27; ++k) sw[co] += hw[co * 32 + k] < 0 ? -hw[co * 32 + k] : hw[co * 32 + k]; }
+    return M == 127 && f[P1_ACC_TAP] < 0 && H == 2 * Hout && W == 2 * Wout && Wout % P1_TW == 0 && Hout % P1_TH == 0 && W % 4 == 0 &&
+           (unsigned long long)n * Hout * Wout < (1ull << 28) &&
+           (pa.img_u8 ? ((uintptr_t)pa.img_u8 & 15) == 0 || !pa.p1_fused && ((uintptr_t)pa.img_u8 & 3) == 0 : ((uintptr_t)pa.img & 15) == 0) &&
+           magic_coeffs_ok(16, M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
+}
 
 // launch plan op i of a pass
 static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t st) {
@@ -553,14 +582,13 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
             pc.k1[co] = fold ? ht[co] * ht[16 + co] : ht[co]; pc.i1[co] = ht[16 + co];
             pc.k2[co] = fold ? ht[32 + co] * ht[48 + co] : ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
         }
-        long long sw[16];
-        for (int co = 0; co < 16; ++co) { sw[co] = 0; for (int k = 0; k < 27; ++k) sw[co] += hw[co * 32 + k] < 0 ? -hw[co * 32 + k] : hw[co * 32 + k]; }
-        const bool lean = fold && !a.acc_tap && H == 2 * a.Hout && W == 2 * a.Wout && a.Wout % P1_TW == 0 && a.Hout % P1_TH == 0 && W % 4 == 0 &&
-                          (unsigned long long)n * a.Hout * a.Wout < (1ull << 28) &&
-                          (pa.img_u8 ? ((uintptr_t)pa.img_u8 & 3) == 0 : ((uintptr_t)img & 15) == 0) &&
-                          magic_coeffs_ok(16, a.M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
+        const bool lean = p1_lean(e, f, pa);
+        a.amax_rw = amax;
+        a.sync = (unsigned*)(amax + e->cap);
         if (lean) {                                                // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
-            for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }
+            for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }   // (i1: the test build's conv_p1_fast_kernel)
+            P1Const pc2 = pc;                                      // tensor-core kernel: MAGIC2 epilogue, first coefficient pre-scaled by 2^-8
+            for (int co = 0; co < 16; ++co) pc2.k1[co] = pc.k1[co] * 0.00390625f;
 #ifdef AYQ_TEST_BUILD
             const bool p1_tc = e->conv_impl >= 1 && !e->p1_dp4a;
 #else
@@ -574,8 +602,13 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                         for (int co = 0; co < 16; ++co)
                             for (int t = 0; t < 9; ++t)            // t = kx * 3 + c
                                 wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
-                if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
-                else CK(launch_k(tc::conv_p1_tc_kernel<false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc, wb));
+                if (pa.p1_fused) {                                 // abs-max inside the kernel, one image ahead (conv_tc.cuh): nb * (n + 1) tickets
+                    const unsigned nblk = (unsigned)(a.Hout / P1_TH) * (unsigned)(n + 1);
+                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                    else CK(launch_k(tc::conv_p1_tc_kernel<false, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                }
+                else if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                else CK(launch_k(tc::conv_p1_tc_kernel<false, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
             }
 #ifdef AYQ_TEST_BUILD
             else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));
@@ -668,12 +701,16 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     float* amax = (float*)(e->ws + e->off_amax);
     const bool prof = e->profiling;
     PassArgs pa{img, img_u8, n, dbox_cls, dets, counts};
+    // fused abs-max + Conv_P1 (one read of the image from HBM instead of two): the lean tensor-core Conv_P1 of the product path
+    pa.p1_fused = e->p1_fuse && !e->p1_dp4a && e->conv_impl >= 1 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1;
+    if (pa.p1_fused) pa.p1_fused = p1_lean(e, e->ops[0].f, pa);
+    e->last_fused = pa.p1_fused;
     int pe = 0;
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
-    CK(cudaMemsetAsync(amax, 0, sizeof(float) * n, st));
+    CK(cudaMemsetAsync(amax, 0, sizeof(float) * e->cap + sizeof(unsigned) * (e->cap + 1), st));   // amax[] and the fused kernel's ticket / band counters
     // The image is read twice (per-image abs-max, then quantise + Conv_P1).  With fp32 images a pass does not fit the L2, so
     // the two kernels are interleaved over chunks of p1_chunk images: the second read of a chunk then comes from the L2.
-    const int chunk = (!prof && !e->debug_sync && !img_u8 && e->p1_chunk > 0 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1) ? e->p1_chunk : 0;
+    const int chunk = (!pa.p1_fused && !prof && !e->debug_sync && !img_u8 && e->p1_chunk > 0 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1) ? e->p1_chunk : 0;
     if (chunk && n > chunk) {
         const size_t per = (size_t)3 * H * W;
         for (int i0 = 0; i0 < n; i0 += chunk) {
@@ -684,7 +721,8 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
             if (rc) return rc;
         }
         pa.p1_img0 = 0; pa.p1_cnt = -1;
-    } else if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
+    } else if (pa.p1_fused) { /* the abs-max runs inside Conv_P1 */ }
+    else if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
     else CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
     const size_t op_first = (chunk && n > chunk) ? 1 : 0;            // Conv_P1 already launched chunk by chunk
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));

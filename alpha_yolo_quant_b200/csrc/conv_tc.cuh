@@ -56,13 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // Same, for waits that are far from the critical path (a producer waiting for a ring slot to drain): back off between probes so
 // that the polling does not compete with the epilogue warps for issue slots.
+// Measured (ncu source view, round 2): with a 96 ns sleep this loop ran ~30 times per wait at ~57 cycles per turn (the hardware
+// wake-up of try_wait fires on unrelated barrier traffic of the CTA) and made up 11 % of ALL instructions the conv kernel
+// issued -- in a kernel whose epilogue is bound by instruction issue.  A producer is a whole ring ahead of the MMA warp, so it can
+// afford to look again only every ~0.5 us.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t it = 0;; ++it) {
-        __nanosleep(96);
+        __nanosleep(512);
         if (mbar_try_wait(bar, parity)) return;
-        if (it > (1u << 25)) __trap();
+        if (it > (1u << 23)) __trap();
     }
+}
+// named barrier of one epilogue group (four warps): id 1.. (0 is __syncthreads)
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -159,20 +167,78 @@ __device__ __forceinline__ void tmem_ld_wait16(int* r) {
 struct P1B { int8_t b[2][4][16][16]; };    // [ox parity][ky2, zero, ky0, ky1][cout][byte position]
 
 #define P1TC_THREADS 288          // warps 0-7: one output pixel each (im2col row, TMEM lane, epilogue); all 9 warps: patch loaders
-template <bool U8>
+// FUSED: the per-image abs-max of quant_matrix() (utils/a.py:4-5) runs INSIDE this kernel, one image ahead of the convolution, so
+// the image is read from HBM once (the second read, by the convolution of the same band 40 tickets later, hits the L2).  Blocks
+// take a ticket (atomic counter = start order): ticket v does (1) the abs-max of band v % nb of image ia = v / nb, published
+// with atomicMax + a per-image band counter, then (2) the convolution of the same band of image ia - 1 once that image's
+// counter shows all nb bands.  A block only ever waits for blocks with SMALLER tickets, which have started and whose step (1)
+// depends on nothing, so the wait always ends (no co-residency assumption).  grid = nb * (n + 1) blocks; a.sync = {ticket,
+// band counters[n]} zeroed (with amax[]) by the host before the launch.
+template <bool U8, bool FUSED>
 __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc,
                                                                 const __grid_constant__ P1B wb) {
     __shared__ __align__(1024) unsigned char sA[2][3][2048];      // [parity][ky2, ky0, ky1][128 rows][16 B]
     __shared__ __align__(128) unsigned char sB[2][4][256];
     __shared__ __align__(16) unsigned sQ[2 * P1_TH + 1][56];       // 224-byte rows (conflict-free word stride 3 across a half warp)
-    __shared__ float2 lut2[AYQ_LUT256];
+    extern __shared__ __align__(128) float lut_rep[];             // per-lane replicated sigmoid table (AYQ_LUTREP_BYTES of dynamic smem)
     __shared__ unsigned qlut[U8 ? 256 : 1];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned fz_s[12];                                 // FUSED: [0] ticket, [1..9] per-warp maxima
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int y0 = blockIdx.y * P1_TH, img = blockIdx.z + a.img0;
+    int y0 = blockIdx.y * P1_TH, img = blockIdx.z + a.img0;
     pdl_trigger();
-    fill_lut256_magic(lut2, a.lut, a.M, tid, P1TC_THREADS);
+    if (FUSED) {
+        pdl_wait();                                               // the host's memset of a.sync / amax and the image are complete
+        const int nb = a.Hout / P1_TH;
+        if (tid == 0) fz_s[0] = atomicAdd(a.sync, 1u);
+        __syncthreads();
+        const unsigned v = fz_s[0];
+        const int ia = (int)(v / (unsigned)nb), band = (int)(v - (unsigned)ia * (unsigned)nb);
+        if (ia < a.n) {                                           // (1) abs-max of rows [band * H / nb, (band + 1) * H / nb) of image ia
+            const int rows = a.H / nb;                            // H == 2 * Hout, Hout % P1_TH == 0: 2 * P1_TH rows per band
+            unsigned m = 0u;
+            if (U8) {
+                const int nvec = rows * a.W / 16;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint4* src = (const uint4*)(a.img_u8 + ((size_t)(ia * 3 + c) * a.H + (size_t)band * rows) * a.W);
+                    for (int i = tid; i < nvec; i += P1TC_THREADS) {
+                        const uint4 q = __ldg(src + i);
+                        m = __vmaxu4(m, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+                    }
+                }
+                m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+            } else {
+                const int nvec = rows * a.W / 4;
+                float fm = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4* src = (const float4*)(a.img + ((size_t)(ia * 3 + c) * a.H + (size_t)band * rows) * a.W);
+#pragma unroll 3
+                    for (int i = tid; i < nvec; i += P1TC_THREADS) {
+                        const float4 q = __ldg(src + i);
+                        fm = fmaxf(fm, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
+                    }
+                }
+                m = __float_as_uint(fm);                          // |x| >= 0: the bit patterns order like the values
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((tid & 31) == 0) fz_s[1 + warp] = m;
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < P1TC_THREADS / 32; ++w) m = max(m, fz_s[1 + w]);
+                const unsigned bits = U8 ? __float_as_uint(__fdiv_rn((float)m, 255.f)) : m;     // max|u8 / 255| = fl32(max(u8) / 255)
+                atomicMax((unsigned*)a.amax_rw + ia, bits);
+                __threadfence();
+                atomicAdd(a.sync + 1 + ia, 1u);
+            }
+        }
+        if (ia == 0) return;                                      // no image -1 to convolve (nothing allocated yet: plain exit)
+        img = ia - 1; y0 = band * P1_TH;
+    }
+    fill_lut_rep(lut_rep, a.lut, a.M, tid, P1TC_THREADS);
     if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];
     if (tid == 0) {
         mbar_init(smem_u32(&bar), 1);
@@ -182,8 +248,22 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    pdl_wait();                                                   // amax[] comes from the abs-max kernel
-    const float amax = a.amax[img];
+    if (!FUSED) pdl_wait();                                       // amax[] comes from the abs-max kernel
+    if (FUSED) {                                                  // (2) wait until every band of image `img` has published its maximum
+        if (tid == 0) {
+            const unsigned nb = (unsigned)(a.Hout / P1_TH);
+            const unsigned* cnt = a.sync + 1 + img;
+            unsigned seen;
+            for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                if (seen >= nb) break;
+                __nanosleep(64);
+                if (spin > (1u << 26)) __trap();                  // seconds: can only be a protocol bug; fail instead of hanging
+            }
+        }
+        __syncthreads();
+    }
+    const float amax = FUSED ? __ldcg(a.amax + img) : a.amax[img];
     const float s = __fmul_rn(__frcp_rn(amax), (float)a.M);
     const bool any = amax > 0.f;
     const size_t cs = (size_t)a.H * a.W;
@@ -285,8 +365,9 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
             tmem_ld_wait16(acc);
             const float half = a.half;
             int r[16];
+            const uint32_t lut_thr = smem_u32(lut_rep) + ((uint32_t)(tid & 31) << 2) + 0x80000000u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = silu_magic(acc[j] + pc.bias[j], pc.k1[j], pc.i1[j], pc.k2[j], lut2, half);
+            for (int j = 0; j < 16; ++j) r[j] = silu_magic2<false>(acc[j] + pc.bias[j], pc.k1[j], pc.k2[j], lut_thr, half);
             const int ox = x0 + 2 * h + e, oy = y0 + ty;
             const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
                                           (uint32_t)(oy >> 1) * (uint32_t)(a.Wout >> 1) + (uint32_t)(ox >> 1)
@@ -316,6 +397,8 @@ struct TcParams {
     int tiles_x, tiles_y, ntiles;
     unsigned mul_x, mul_y;         // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y)  (0 when the divisor is 1)
     int role_hi;                   // conv_tma: control warps on the highest warp ids (see the kernel)
+    int nbuf;                      // conv_tma: TMEM accumulator buffers per pipeline
+    int nq;                        // conv_tma: producer -> ring -> issuer chains per pipeline (1 or 2)
 };
 
 constexpr int TC_PRODUCERS = 128;
@@ -394,6 +477,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
                                              const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u, 0u}) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
+    const uint32_t lut_thr = smem_u32(lut_s) + ((threadIdx.x & 31u) << 2) + 0x80000000u;     // MAGIC2 (loop invariant, hoisted by the compiler)
     int r[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -402,7 +486,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
             acc[4 * q + j] = v;
-            if (EPI == 0 && FAST == 2) r[4 * q + j] = silu_magic(v, cf.k1[j], cf.i1[j], cf.k2[j], (const float2*)lut_s, half);   // b = bias + magic, i1 = -k1p * C
+            if (EPI == 0 && FAST >= 2) r[4 * q + j] = silu_magic2<FAST == 3>(v, cf.k1[j], cf.k2[j], lut_thr, half, M);   // FAST 2: b = bias + magic; k1 = k1p * 2^-8
             else if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
                                               : silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
             else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127f(__int2float_rn(v), cf.k1[j], half)
@@ -414,11 +498,11 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         const uint32_t npix = so.plane16 >> 4;
         const uint32_t off = (uint32_t)(c0 >> 4) * so.plane16 + so.pix16;
         const uint32_t ps_off = (uint32_t)(c0 >> 4) * so.ps_plane16 + so.ps_pix16;
-        if (EPI == 0 && FAST == 2 && a.gen_outs) {
+        if (EPI == 0 && FAST >= 2 && a.gen_outs) {
             // general output list.  A requantised copy (requantize(silu, old, new) with SCALAR coefficients, e.g. :741, :903) is
             // a function of the 8-bit SiLU result alone: one byte load from the 256-entry table the prologue built with the
             // very same requant8() arithmetic (smem right behind the sigmoid table).
-            const unsigned char* rq = (const unsigned char*)lut_s + AYQ_LUT256 * 8 + 128;
+            const unsigned char* rq = (const unsigned char*)lut_s + AYQ_LUTREP_BYTES + 128;
             const uint4 vid = make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]));
             for (int o = 0; o < a.nout; ++o) {
                 const OutSpec& os = a.out[o];
@@ -449,7 +533,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             return;
         }
         if (EPI != 2) {
-            const uint4 v = FAST == 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
+            const uint4 v = FAST >= 2 ? make_uint4(pack4_sat(r[0], r[1], r[2], r[3]), pack4_sat(r[4], r[5], r[6], r[7]), pack4_sat(r[8], r[9], r[10], r[11]), pack4_sat(r[12], r[13], r[14], r[15]))
                                       : make_uint4(pack4(r[0], r[1], r[2], r[3]), pack4(r[4], r[5], r[6], r[7]), pack4(r[8], r[9], r[10], r[11]), pack4(r[12], r[13], r[14], r[15]));
             if (EPI == 0 && so.mode != 0u) *(uint4*)((int8_t*)a.out[a.nout - 1].base + ps_off) = v;   // phase-split copy (alone, or next to the plain tensor)
             if (EPI != 0 || so.mode != 1u) *(uint4*)((int8_t*)a.out[0].base + off) = v;

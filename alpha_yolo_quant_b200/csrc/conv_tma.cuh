@@ -35,13 +35,15 @@ namespace tc {
 constexpr int TMA_MAX_MAPS = 8;
 #define AYQ_MAX_OUT_ 3
 constexpr int TMA_MAX_OPS = 56;
-constexpr int TMA_MAX_STAGES = 24;
-// block = 256 + 256 * EG threads: warps 0-1 MMA issuers, 2-5 TMA producers, 6-7 idle, then EG epilogue groups (4 warps) per pipeline
+constexpr int TMA_MAX_STAGES = 40;
+// block = 256 + 256 * EG threads: warps 0-1 and 6-7 MMA issuers (two per pipeline), 2-5 TMA producers, then EG epilogue groups (4 warps) per pipeline
 
 struct TmaOp { int map; int dx, dy, p0; uint32_t dst_off; };          // box origin offsets (tap - pad), first plane, byte offset in the slot
 struct TmaStage { int op0, nops, nchunks, chunk0; };
-constexpr int TMA_MAX_HMMA = 40;
-struct HaloMma { uint32_t a_off_lbo; uint32_t b_chunk; };              // A start (16-byte units, low 16 bits) | LBO (16-byte units) << 16; first B chunk
+constexpr int TMA_MAX_HMMA = 80;
+// one K = 32 MMA of a halo tile = two K chunks: A start (16-byte units, low 16 bits) | LBO (16-byte units) << 16, and the same for
+// B relative to the resident weights (first chunk * N | chunk distance * N << 16)
+struct HaloMma { uint32_t a_off_lbo; uint32_t b_off_lbo; };
 struct TmaPlan {
     int nstages, nops, stride, slot_chunks;                            // slot_chunks = K chunks one ring slot can hold
     int merged_cx;                                                     // 1: stride-1 conv, rank-4 maps with (channel, x) merged into one 16*W byte row
@@ -83,8 +85,12 @@ __device__ __forceinline__ uint32_t elect_one() {          // one lane of the (f
 // EG = epilogue groups (of 4 warps) per pipeline = TMEM accumulator buffers per pipeline when EG >= 2 (group k owns buffer k and
 // every EG-th tile of its pipeline).  3 for cout <= 32 (1024 threads at <= 64 registers: these layers are bound by instruction
 // issue in the epilogue, more resident epilogue warps hide its latencies), 2 for the other compile-time-cout kernels, 1 otherwise.
-#define TMA_EG(NBC) ((NBC) == 1 || (NBC) == 2 ? 3 : ((NBC) > 0 ? 2 : 1))
-constexpr int TMA_NB = 3;                                          // barrier slots per pipeline for the accumulator buffers
+// NBC == 0 (cout 128 / 256, coefficients from shared memory): two groups per pipeline as well, but they SPLIT THE COLUMNS of the
+// same tile (group k drains channels [k * N / 2, (k + 1) * N / 2)): sixteen epilogue warps instead of eight on the layers
+// whose tiles are the longest to drain, without a second accumulator per group (cout 256 fills the TMEM with one per pipeline).
+#define TMA_EG(NBC) ((NBC) == 1 || (NBC) == 2 ? 3 : 2)
+#define TMA_CSPLIT(NBC) ((NBC) == 0)
+constexpr int TMA_NB = 6;                                          // barrier slots per pipeline for the accumulator buffers (ring of up to 6)
 template <int NBC, int EPI, int FAST, int EG = TMA_EG(NBC)>
 __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ TcParams tp,
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
@@ -111,7 +117,11 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     float* lut_s = (float*)(bias_s + N);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
     const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2 * TMA_NB]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4 * TMA_NB]);
-    const int nbuf = EG >= 2 ? EG : (tp.tmem_cols >= 4 * N ? 2 : 1);   // TMEM accumulator buffers per pipeline (cout 256: one)
+    // TMEM accumulator ring of a pipeline: tile j of the pipeline (j = 0, 1, ...) lands in buffer j % nbuf and is drained by
+    // epilogue group j % EG.  nbuf = 2 * EG where the 512 columns allow it: a group then never waits for the refill of the buffer
+    // it has just handed back (barrier hand-off + MMA issue + MMA execution, several hundred cycles) -- its next tile is already
+    // complete in the other buffer.
+    const int nbuf = tp.nbuf;
 
     pdl_trigger();
     // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
@@ -119,19 +129,19 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         if (FAST) {                                                 // folded coefficients: rows 0 / 2 hold k * 2^-s (exact)
             for (int i = tid; i < N; i += TMA_THREADS) {
                 const float k1p = __fmul_rn(a.tab[i], a.tab[N + i]);
-                tab_s[i] = k1p;
+                tab_s[i] = FAST >= 2 ? __fmul_rn(k1p, 0.00390625f) : k1p;        // MAGIC2: coefficient of the first requant pre-scaled by 2^-8 (exact)
                 tab_s[2 * N + i] = __fmul_rn(a.tab[2 * N + i], a.tab[3 * N + i]);
-                tab_s[N + i] = FAST == 2 ? -__fmul_rn(k1p, AYQ_MAGIC_F) : 0.f; tab_s[3 * N + i] = 0.f;
+                tab_s[N + i] = 0.f; tab_s[3 * N + i] = 0.f;
             }
         } else {
             for (int i = tid; i < 4 * N; i += TMA_THREADS) tab_s[i] = a.tab[i];
         }
         for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i] + (FAST == 2 ? AYQ_MAGIC_I : 0);
     }
-    if (EPI == 0 && FAST == 2) {
-        fill_lut256_magic((float2*)lut_s, a.lut, a.M, tid, TMA_THREADS);
+    if (EPI == 0 && FAST >= 2) {
+        fill_lut_rep(lut_s, a.lut, a.M, tid, TMA_THREADS);         // per-lane replicated sigmoid table (fixedpoint.cuh: silu_magic2)
         if (a.gen_outs) {                                          // 256-byte table per requantised output: index = SiLU result + 128
-            unsigned char* rq = (unsigned char*)lut_s + AYQ_LUT256 * 8;
+            unsigned char* rq = (unsigned char*)lut_s + AYQ_LUTREP_BYTES;
             for (int i = tid; i < 256 * a.nout; i += TMA_THREADS) {
                 const OutSpec& os = a.out[i >> 8];
                 rq[i] = (unsigned char)(os.mode == 1 ? requant8((float)((i & 255) - 128), os.k, os.inv, a.M) : ((i & 255) - 128));
@@ -141,7 +151,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     else if (EPI == 0) fill_lut256(lut_s, a.lut, a.M, tid, TMA_THREADS);
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2 * TMA_NB; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        for (int b = 0; b < 2 * TMA_NB; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, TMA_CSPLIT(NBC) ? 128 * EG : 128); }
         if (!tp.resident_b) mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -168,75 +178,77 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     const uint32_t tmem_base = tmem_base_s;
     pdl_wait();                                                     // activations of the previous layer are complete from here on
 
-    // Two independent pipelines share the CTA: pipeline m (m = 0, 1) = producer warp 2+m -> ring slots [m*NSH, (m+1)*NSH) ->
-    // MMA issuer warp m -> TMEM buffer m -> epilogue group m, and handles the tiles i with i % 2 == m.  A single issuer's
-    // per-tile loop (barrier probes, fences, elect, descriptor moves to uniform registers, MMAs, commits) is a serial chain
-    // of several hundred cycles; two pipelines overlap their chains, and private rings keep every barrier strictly in-order
-    // for its one producer / one consumer (parity waits cannot alias).
-    const int NSH = NS >> 1;
+    // Two pipelines share the CTA: pipeline m (m = 0, 1) owns the tiles i with i % 2 == m, its accumulator ring in TMEM and its EG
+    // epilogue groups.  Each pipeline is fed by TWO independent chains (q = 0, 1: the pipeline's even / odd tiles), each chain =
+    // one TMA producer warp -> a private ring of NSQ = NS / 4 smem slots -> one MMA issuer warp.  The per-tile issue path of an
+    // issuer (barrier probes, fences, elect, descriptor moves to uniform registers, MMAs, commits) is a serial chain of ~200
+    // instructions that shares a scheduler with six epilogue warps (measured ~1100 busy cycles per tile); four chains overlap
+    // them.  Private rings keep every mbarrier strictly in order for its one producer and one consumer: a parity wait may never
+    // skip a phase (a consumer that has not seen phase 0 of a barrier finds "parity 1" already complete on a fresh barrier).
+    const int nq = tp.nq;                                         // chains per pipeline: 2, or 1 when the pipeline has a single accumulator (cout 256)
+    const int NSQ = NS / (2 * nq);
     if (warp >= 2 && warp < 6) {
-        // ===== TMA producers of pipeline m (two warps per pipeline, q = 0 / 1 take the even / odd stages of its ring; NSH is
-        // even, so a slot always belongs to the same producer): warp-uniform control flow, one elected lane issues (all
-        // operands of the tensor loads live in uniform registers: no per-lane waterfall loops) =====
+        // ===== TMA producer of chain (m, q): warp-uniform control flow, one elected lane issues (all operands of the tensor loads
+        // live in uniform registers: no per-lane waterfall loops) =====
         const int m = (warp - 2) & 1, q = (warp - 2) >> 1;
         const int nstages = pl.nstages, stride = pl.stride;
-        const int slot0 = m * NSH;
-        int slot = 0, turn = 0;
+        const int slot0 = (nq * m + q) * NSQ;
+        int slot = 0;
         uint32_t ephase = 1;                                       // fresh barrier: parity 1 passes immediately
         long long d_wait = 0, d_t0 = AYQ_CLK(a);
-        for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
+        for (int t = q < nq ? blockIdx.x + (m + 2 * q) * gridDim.x : tp.ntiles; t < tp.ntiles; t += 2 * nq * gridDim.x) {
             const TileCoord tc0 = tile_coord(t, tp);
             const int xs = tc0.x0 * stride, ys = tc0.y0 * stride;
             for (int s = 0; s < nstages; ++s) {
-                if (turn == q) {
-                    const TmaStage sg = pl.st[s];
-                    const int gs = slot0 + slot;
-                    const long long w0 = AYQ_CLK(a);
-                    mbar_wait_relaxed(empty0 + 8 * gs, ephase);
-                    if (AYQ_DBG(a)) d_wait += clock64() - w0;
-                    if (elect_one()) {
-                        const uint32_t bar = full0 + 8 * gs;
-                        const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
-                        mbar_arrive_expect_tx(bar, (pl.halo ? (uint32_t)pl.halo_tx_bytes : (uint32_t)sg.nchunks * 2048u) + (tp.resident_b ? 0u : nch_b * N * 16u));
-                        const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
-                        for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
-                            const TmaOp op = pl.op[o];
-                            if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
-                            else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
-                        }
-                        if (!tp.resident_b)
-                            bulk_g2s(smem_u32(sB) + gs * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
+                const TmaStage sg = pl.st[s];
+                const int gs = slot0 + slot;
+                const long long w0 = AYQ_CLK(a);
+                mbar_wait_relaxed(empty0 + 8 * gs, ephase);
+                if (AYQ_DBG(a)) d_wait += clock64() - w0;
+                if (elect_one()) {
+                    const uint32_t bar = full0 + 8 * gs;
+                    const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
+                    mbar_arrive_expect_tx(bar, (pl.halo ? (uint32_t)pl.halo_tx_bytes : (uint32_t)sg.nchunks * 2048u) + (tp.resident_b ? 0u : nch_b * N * 16u));
+                    const uint32_t dst0 = smem_u32(sA) + gs * a_slot_bytes;
+                    for (int o = sg.op0; o < sg.op0 + sg.nops; ++o) {
+                        const TmaOp op = pl.op[o];
+                        if (pl.merged_cx) tma_load_4d(dst0 + op.dst_off, &maps.m[op.map], (xs + op.dx) * 16, ys + op.dy, tc0.img0, op.p0, bar);
+                        else tma_load_5d(dst0 + op.dst_off, &maps.m[op.map], 0, xs + op.dx, ys + op.dy, tc0.img0, op.p0, bar);
                     }
-                    __syncwarp();
+                    if (!tp.resident_b)
+                        bulk_g2s(smem_u32(sB) + gs * b_slot_bytes, a.w + (size_t)sg.chunk0 * N * 16, nch_b * N * 16u, bar);
                 }
-                turn ^= 1;
-                if (++slot == NSH) { slot = 0; ephase ^= 1; }
+                __syncwarp();
+                if (++slot == NSQ) { slot = 0; ephase ^= 1; }
             }
         }
         if (AYQ_DBG(a) && lane == 0 && q == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
-    } else if (warp < 2) {
-        // ===== MMA issuer of pipeline m: warp-uniform control flow, one elected lane issues; the descriptor low words
-        // (address | LBO) are stepped with 32-bit adds =====
-        const int m = warp;
+    } else if (warp < 2 || warp == 6 || warp == 7) {
+        // ===== MMA issuer of chain (m, par): warp-uniform control flow, one elected lane issues; the descriptor low words (address |
+        // LBO) are stepped with 32-bit adds.  Warps m and 6 + m issue the even / odd tiles of pipeline m from their private rings; the
+        // two share the pipeline's accumulator ring (tile j -> buffer j % nbuf), whose barriers each of them always finds in the
+        // phase it expects: a buffer cannot be released twice before the issuer that waits for it has refilled it. =====
+        const int m = warp & 1, par = warp >= 6 ? 1 : 0;
         const uint32_t idesc = make_idesc_i8(N);
         const int nstages = pl.nstages;
         if (tp.resident_b) mbar_wait(wfull, 0);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1 (bits 32.. of make_desc)
         const uint32_t h_hi = (160u >> 4) | (1u << 14);            // halo mode: 8-pixel row groups are one halo row (10 pixels) apart
         const uint32_t a_lo0 = ((smem_u32(sA) & 0x3ffffu) >> 4) | ((2048u >> 4) << 16);
-        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3ffffu) >> 4) | ((((uint32_t)N * 16u) >> 4) << 16);
+        const uint32_t b_base = (smem_u32(sB) & 0x3ffffu) >> 4;    // halo mode: the plan's words carry the chunk offset and the LBO
+        const uint32_t b_lo0 = b_base | ((((uint32_t)N * 16u) >> 4) << 16);
         const uint32_t a_step = a_slot_bytes >> 4, b_step = tp.resident_b ? 0u : (b_slot_bytes >> 4);
         const uint32_t b_pair = 2u * (uint32_t)N;                  // two K chunks of B, in 16-byte units
         const TmaStage sg0 = pl.st[0];
-        const int slot0 = m * NSH;
-        int slot = 0, buf = 0;
-        uint32_t fphase = 0, ephase = 7;                           // bit buf = parity to wait for on tempty[m][buf]; fresh barriers pass parity 1
+        const int slot0 = (nq * m + par) * NSQ;
+        int slot = 0, buf = par;                                   // chain `par` owns the accumulators j % nbuf of its tiles j = par, par + nq, ...: with
+                                                                   // nq = 2 and nbuf even, the even / odd buffers -- private, like its ring slots
+        uint32_t fphase = 0, ephase = 1;                           // parity to wait for on tempty[m][buf]: fresh barriers pass parity 1; flips per ring turn
         long long d_we = 0, d_wf = 0, d_t0 = AYQ_CLK(a);
-        for (int t = blockIdx.x + m * gridDim.x; t < tp.ntiles; t += 2 * gridDim.x) {
+        for (int t = par < nq ? blockIdx.x + (m + 2 * par) * gridDim.x : tp.ntiles; t < tp.ntiles; t += 2 * nq * gridDim.x) {
             const long long w0 = AYQ_CLK(a);
-            mbar_wait(tempty0 + 8 * (TMA_NB * m + buf), (ephase >> buf) & 1u);
+            mbar_wait(tempty0 + 8 * (TMA_NB * m + buf), ephase);
             if (AYQ_DBG(a)) d_we += clock64() - w0;
-            ephase ^= 1u << buf;
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)((m * nbuf + buf) * N);
             uint32_t accum = 0;
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                         const int n_hmma = pl.n_hmma;
                         for (int j = 0; j < n_hmma; ++j) {
                             const HaloMma hmj = pl.hm[j];
-                            mma_i8_lh(dcol, abase + hmj.a_off_lbo, h_hi, b_lo0 + hmj.b_chunk * (uint32_t)N, d_hi, idesc, acc);
+                            mma_i8_lh(dcol, abase + hmj.a_off_lbo, h_hi, b_base + hmj.b_off_lbo, d_hi, idesc, acc);
                             acc = 1;
                         }
                     } else {
@@ -272,36 +284,44 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 }
                 __syncwarp();
                 accum = 1;
-                if (++slot == NSH) { slot = 0; fphase ^= 1; }
+                if (++slot == NSQ) { slot = 0; fphase ^= 1; }
             }
-            if (++buf == nbuf) buf = 0;
+            buf += nq;
+            if (buf >= nbuf) { buf -= nbuf; ephase ^= 1u; }
         }
-        if (AYQ_DBG(a) && lane == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
+        if (AYQ_DBG(a) && lane == 0 && par == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int gq = (warp - 8) >> 2;
         const int grp = gq / EG, gk = gq - grp * EG;              // pipeline (tile parity) this group drains; its index inside the pipeline
-        const int tstep = 2 * EG;                                // EG >= 2: group (grp, gk) owns TMEM buffer gk and every EG-th tile of the pipeline
+        constexpr bool CS = TMA_CSPLIT(NBC);                     // column split: every group of the pipeline drains every tile (its share of the channels)
+        const int tstep = CS ? 2 : 2 * EG;                       // otherwise group gk takes every EG-th tile of the pipeline
         const int row = ((warp & 3) << 5) | lane;                // TMEM lane == GEMM row; warp w may touch lanes 32*(w%4)..
         const int dx = row & ((1 << tp.bw_log) - 1), dy = (row >> tp.bw_log) & ((1 << tp.bh_log) - 1), dn = row >> (tp.bw_log + tp.bh_log);
         const uint32_t lane_quad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t tphase = 0;                                     // bit buf = parity to wait for on tfull[grp][buf]
-        int buf = EG >= 2 ? gk : 0;
+        uint32_t tphase = 0;                                     // parity to wait for on tfull[grp][buf] (flips per ring turn)
+        int buf = CS ? 0 : gk;                                   // tile j = gk, gk + EG, ... of the pipeline -> buffer j % nbuf
+        while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         long long d_wt = 0, d_t0 = AYQ_CLK(a);
-        for (int t = blockIdx.x + (grp + 2 * gk) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
+        for (int t = blockIdx.x + (grp + (CS ? 0 : 2 * gk)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
             const uint32_t tfull_b = tfull0 + 8 * (TMA_NB * grp + buf), tempty_b = tempty0 + 8 * (TMA_NB * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
-            const bool valid = img < a.n;
+            const bool valid = img < a.n && oy < a.Hout;          // overhanging tiles: images past the batch, rows past the map (halo mode)
             const StoreOff so = FAST ? store_off(a, img, oy, ox) : StoreOff{0u, 0u, 0u, 0u, 0u};   // per-tile part of the store addresses
             const long long w0 = AYQ_CLK(a);
-            mbar_wait(tfull_b, (tphase >> buf) & 1u);
-            tphase ^= 1u << buf;
+            // ONE warp of the group polls the accumulator barrier; the other three park in a hardware barrier that costs no issue
+            // slots (every polling warp re-executes its probe loop whenever any barrier of the CTA changes: measured 8 % of all
+            // issued instructions with four pollers per group).
+            if ((warp & 3) == 0) mbar_wait(tfull_b, tphase);
+            group_bar_sync(1 + gq, 128);
             if (AYQ_DBG(a)) d_wt += clock64() - w0;
             tc_fence_after();
             int accA[16], accB[16];
-            tmem_ld16(lane_base, accA);
+            const int nbh = CS ? (N / 16) / EG : N / 16;          // 16-channel groups this epilogue group drains (even, checked by the host)
+            const int g0 = CS ? gk * nbh : 0;
+            tmem_ld16(lane_base + (uint32_t)(g0 * 16), accA);
             if (NBC > 0) {
 #pragma unroll
                 for (int gch = 0; gch < NBC; ++gch) {
@@ -313,8 +333,8 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
                 }
             } else {
-                const int nb = N / 16;                                   // even, checked by the host
-                for (int gch = 0; gch < nb; gch += 2) {
+                const int nb = g0 + nbh;
+                for (int gch = g0; gch < nb; gch += 2) {
                     tmem_ld_wait16(accA);
                     tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
                     if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
@@ -324,7 +344,8 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
                 }
             }
-            if (EG == 1 && nbuf == 2) buf ^= 1;
+            buf += CS ? 1 : EG;
+            while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         }
         if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gk == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
     }
@@ -356,7 +377,7 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     int gen_outs = 0;         // MAGIC with a general output list
 };
 
-struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 2; int budget_kb = 208; int resident_kb = 96; int role_hi = 0; };
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 1; int budget_kb = 208; int resident_kb = 96; int role_hi = 0; int nbuf_mul = 2; };
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
 template <int FAST>
@@ -368,20 +389,27 @@ static inline TmaKernel tma_pick_t(int N, int epi) {
         case 32: return conv_tma_kernel<2, 0, FAST>;
         case 64: return conv_tma_kernel<4, 0, FAST>;
         case 80: return conv_tma_kernel<5, 0, FAST>;
-        default: return (N % 32 == 0) ? conv_tma_kernel<0, 0, FAST> : nullptr;
+        default: return (N % 64 == 0) ? conv_tma_kernel<0, 0, FAST> : nullptr;   // column split: two groups x an even number of 16-channel groups
         }
     }
-    constexpr int F = FAST ? 1 : 0;                               // the magic variant only exists for the SiLU epilogue
-    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, F> : (N % 32 == 0 ? conv_tma_kernel<0, 1, F> : nullptr);
-    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, F> : (N % 32 == 0 ? conv_tma_kernel<0, 2, F> : nullptr);
+    constexpr int F = FAST ? 1 : 0;                               // the magic / wide variants only exist for the SiLU epilogue
+    if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, F> : (N % 64 == 0 ? conv_tma_kernel<0, 1, F> : nullptr);
+    if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, F> : (N % 64 == 0 ? conv_tma_kernel<0, 2, F> : nullptr);
     return nullptr;
 }
-static inline TmaKernel tma_pick(int N, int epi, int fast) { return fast == 2 ? tma_pick_t<2>(N, epi) : fast ? tma_pick_t<1>(N, epi) : tma_pick_t<0>(N, epi); }
+static inline TmaKernel tma_pick(int N, int epi, int fast) {
+    return fast == 3 ? tma_pick_t<3>(N, epi) : fast == 2 ? tma_pick_t<2>(N, epi) : fast ? tma_pick_t<1>(N, epi) : tma_pick_t<0>(N, epi);
+}
 // FAST epilogue: clamp 127 (16-bit logits: 32767), a single identity output, no accumulator tap
 // epilogue groups per pipeline of the kernel tma_pick() returns for this cout (must mirror TMA_EG / the switch in tma_pick_t)
 static inline int tma_eg(int N, int epi) {
-    if (epi == 0) return (N == 16 || N == 32) ? 3 : ((N == 64 || N == 80) ? 2 : 1);
-    return (epi == 1 && N == 64) || (epi == 2 && N == 80) ? 2 : 1;
+    if (epi == 0) return (N == 16 || N == 32) ? 3 : 2;
+    return 2;
+}
+// column split (TMA_CSPLIT): the generic-cout kernels; their groups share every tile, so the accumulator ring is per pipeline
+static inline bool tma_csplit(int N, int epi) {
+    if (epi == 0) return !(N == 16 || N == 32 || N == 64 || N == 80);
+    return !((epi == 1 && N == 64) || (epi == 2 && N == 80));
 }
 static inline bool tma_fast(const ConvArgs& a) {
     if (a.acc_tap) return false;
@@ -434,7 +462,7 @@ static inline void tma_init(TmaState& s) {
     const int ns[] = {16, 32, 64, 80, 128};
     for (int epi = 0; epi < 3; ++epi)
         for (int N : ns)
-            for (int fast = 0; fast < 3; ++fast) {
+            for (int fast = 0; fast < 4; ++fast) {
                 TmaKernel k = tma_pick(N, epi, fast);
                 if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
             }
@@ -443,6 +471,7 @@ static inline void tma_init(TmaState& s) {
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);
     if (const char* ev = getenv("AYQ_ROLE_HI")) s.role_hi = atoi(ev);
+    if (const char* ev = getenv("AYQ_NBUF_MUL")) s.nbuf_mul = atoi(ev);   // 1: one accumulator buffer per epilogue group (round-1 behaviour)
     if (const char* ev = getenv("AYQ_SMEM_KB")) s.budget_kb = atoi(ev);          // experiments: smaller CTAs let consecutive kernels co-reside
     if (const char* ev = getenv("AYQ_RESIDENT_KB")) s.resident_kb = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
     void* fn = nullptr;
@@ -468,9 +497,14 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     for (int o = 0; o < a.nout; ++o) any_up |= a.out[o].up == 1;
     const bool magic = !a.acc_tap && (unsigned long long)a.n * a.cout * a.Hout * a.Wout * (any_up ? 4 : 1) < (1ull << 32) &&
                        magic_epilogue_ok(a, h_tab, h_bias, h_lut, h_w, (a.nkc + 1) & ~1);
-    const bool fast = magic || tma_fast(a);                       // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
-    L.fast = magic ? 2 : fast ? 1 : 0;
-    L.gen_outs = magic && !tma_fast(a) ? 1 : 0;                   // beyond "one identity output (+ phase-split copy)"
+    // WIDE form of the same epilogue (fixedpoint.cuh): any clamp (K = 8 / 6 / 4), any accumulator range, explicit result clamps
+    // (used where the plain FAST epilogue does not apply -- another clamp, or a general output list; where it does, FAST keeps its
+    // 1 KB table, which matters for the ring depth of exactly these large-K layers: measured)
+    const bool wide = !magic && a.epi == 0 && !a.acc_tap && h_lut && a.M <= 127 && (a.M != 127 || !tma_fast(a)) && !getenv("AYQ_NO_WIDE") &&
+                      (unsigned long long)a.n * a.cout * a.Hout * a.Wout * (any_up ? 4 : 1) < (1ull << 32);
+    const bool fast = magic || wide || tma_fast(a);               // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
+    L.fast = magic ? 2 : wide ? 3 : fast ? 1 : 0;
+    L.gen_outs = (magic || wide) && !tma_fast(a) ? 1 : 0;         // beyond "one identity output (+ phase-split copy)"
     if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, 0)) return 0;
     tc::TcParams& tp = L.tp;
     tp.role_hi = s.role_hi;
@@ -489,55 +523,96 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     tp.nkc_pad = (a.nkc + 1) & ~1;
     // ring slot = 32 KB / 16 KB of A, or the whole (small) K extent: small slots leave room for a deep ring
     const int slot_cap = N <= 64 ? 16 : 8;
-    const int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
+    int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
+    {   // the ring needs at least four slots (two per pipeline): shrink the slot until they fit next to the tables / resident weights
+        const size_t lut_b = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;
+        const size_t fixed_b = (size_t)N * 20 + lut_b + 64, w_b = (size_t)tp.nkc_pad * N * 16;
+        const bool res = w_b <= (size_t)s.resident_kb * 1024;
+        // ... and prefer eight (two per chain, so that a chain can load its next stage while the current one is multiplied) as long as
+        // a slot keeps at least four K chunks
+        while (slot_chunks > 2) {
+            const size_t per = (size_t)slot_chunks * 2048 + (res ? 0 : (size_t)slot_chunks * N * 16);
+            const size_t fit = ((size_t)s.budget_kb * 1024 - fixed_b - (res ? w_b : 0)) / per;
+            if (fit >= 8 || (fit >= 4 && slot_chunks <= 4)) break;
+            if (fit >= 4 && (tp.nkc_pad + slot_chunks / 2 - 1) / (slot_chunks / 2) > tc::TMA_MAX_STAGES - 2) break;   // stage table size
+            slot_chunks = (slot_chunks / 2 + 1) & ~1;
+            if (slot_chunks < 2) slot_chunks = 2;
+        }
+    }
     tp.KS = slot_chunks; tp.nst = 0; tp.lag = 0;
     int cols = 32;
     const int eg = tma_eg(N, a.epi);
-    while (cols < (eg >= 2 ? 2 * eg : (4 * N <= 512 ? 4 : 2)) * N) cols <<= 1;   // two pipelines x EG accumulator buffers (cout 128: two, 256: one)
+    int nbuf = tma_csplit(N, a.epi) ? 2 : s.nbuf_mul * eg;        // accumulator ring per pipeline: two buffers per epilogue group ...
+    while (nbuf > 1 && 2 * nbuf * N > 512) --nbuf;                // ... as far as the 512 TMEM columns go (cout 80: three, 256: one)
+    if (nbuf > tc::TMA_NB) nbuf = tc::TMA_NB;
+    tp.nq = nbuf >= 2 && !getenv("AYQ_ONE_ISSUER") ? 2 : 1;       // two producer -> ring -> issuer chains per pipeline, each with private accumulators
+    if (tp.nq == 2) nbuf &= ~1;
+    tp.nbuf = nbuf;
+    while (cols < 2 * nbuf * N) cols <<= 1;                       // two pipelines x nbuf accumulators
     tp.tmem_cols = cols;
 
     tc::TmaPlan& pl = L.pl;
     pl.halo = 0; pl.n_hmma = 0; pl.halo_tx_bytes = 0;
     L.smem = 0;
     // ---- halo mode: 3x3 stride-1 convs whose map tiles into 8 x 16 pixel boxes ----
-    if (a.stride == 1 && a.Wout % 8 == 0 && a.Hout % 16 == 0 && a.Win == a.Wout && a.Hin == a.Hout && a.nkc >= 9 && tp.nkc_pad * N * 16 <= s.resident_kb * 1024) {
+    // Hout need not be a multiple of 16: the last row of tiles overhangs (TMA zero-fills the reads, the epilogue masks the stores)
+    // as long as at least 80 % of the GEMM rows stay useful (40 x 40 maps: 83 %).
+    const int halo_ty = (a.Hout + 15) / 16;
+    if (a.stride == 1 && a.Wout % 8 == 0 && a.Hout * 5 >= halo_ty * 16 * 4 && a.Win == a.Wout && a.Hin == a.Hout && a.nkc >= 9 &&
+        tp.nkc_pad * N * 16 <= s.resident_kb * 1024) {
         const int HW = 10, HH = 18, PLANE16 = HW * HH;           // halo pixels per plane (= 16-byte units)
-        struct Blk { int seg, p0, np; uint32_t reg16; };
+        struct Blk { int seg, p0, np, i0; uint32_t reg16; };
         Blk blk[8];
         int nblk = 0, i = 0;
         uint32_t reg16 = 0;                                       // running region start, 16-byte units
         bool ok = true;
-        int addr16[160];
         while (ok && i < a.nkc) {                                 // a block = 9 taps (raster order) x np planes of one buffer segment
             int np = 1;
             while (i + np < a.nkc && h_kc[i + np].pad_ == h_kc[i].pad_ && h_kc[i + np].dy == h_kc[i].dy && h_kc[i + np].dx == h_kc[i].dx &&
                    h_kc[i + np].plane == h_kc[i].plane + np) ++np;
-            if (nblk == 8 || i + 9 * np > a.nkc || a.nkc > 160 || np < s.halo_min_np) { ok = false; break; }
+            if (nblk == 8 || i + 9 * np > a.nkc || a.nkc > 2 * tc::TMA_MAX_HMMA || np < s.halo_min_np) { ok = false; break; }
             for (int t = 0; t < 9 && ok; ++t)
                 for (int q = 0; q < np && ok; ++q) {
                     const KChunk& k = h_kc[i + t * np + q];
                     if (k.pad_ != h_kc[i].pad_ || k.plane != h_kc[i].plane + q || k.dy != t / 3 - 1 || k.dx != t % 3 - 1) ok = false;
-                    addr16[i + t * np + q] = (int)reg16 + q * PLANE16 + (t / 3) * HW + (t % 3);
                 }
-            blk[nblk].seg = h_kc[i].pad_; blk[nblk].p0 = h_kc[i].plane; blk[nblk].np = np; blk[nblk].reg16 = reg16;
+            blk[nblk].seg = h_kc[i].pad_; blk[nblk].p0 = h_kc[i].plane; blk[nblk].np = np; blk[nblk].reg16 = reg16; blk[nblk].i0 = i;
             ++nblk;
             reg16 += (uint32_t)((np * PLANE16 + 7) & ~7);         // keep every box start 128-byte aligned
             i += 9 * np;
         }
-        const int npairs = (a.nkc + 1) / 2;
-        if (ok && npairs <= tc::TMA_MAX_HMMA && nblk <= tc::TMA_MAX_MAPS) {
-            for (int j = 0; j < npairs && ok; ++j) {
-                const int c0 = 2 * j, c1 = 2 * j + 1;
-                const int lbo = c1 < a.nkc ? addr16[c1] - addr16[c0] : 1;     // odd tail: second half = any valid smem x zero weights
-                if (lbo <= 0 || lbo >= (1 << 14) || addr16[c0] >= (1 << 14)) ok = false;
-                pl.hm[j].a_off_lbo = (uint32_t)addr16[c0] | ((uint32_t)lbo << 16);
-                pl.hm[j].b_chunk = (uint32_t)c0;
+        // Pair the K chunks into K = 32 MMAs.  Chunk (block b, tap t, plane q) sits at A address reg16_b + q * PLANE16 + tap offset and
+        // at B index i0_b + t * np_b + q.  Both descriptors need a POSITIVE distance from the first to the second chunk of a
+        // pair: planes (q, q + 1) of one tap pair up (A: one plane apart, B: adjacent); what is left over when np is odd -- one
+        // chunk per tap, all of them when the input has 16 channels -- is paired in (block, tap) order, where A addresses and
+        // B indices both increase; a last odd chunk meets the zero chunk that pads the weights to an even count.
+        int npairs = 0;
+        struct Single { int a16, bidx; };
+        Single singles[2 * tc::TMA_MAX_HMMA];
+        int nsingle = 0;
+        auto add_pair = [&](int a0, int a1, int b0, int b1) {
+            const int lbo = a1 - a0, dch = b1 - b0;
+            if (npairs >= tc::TMA_MAX_HMMA || lbo <= 0 || lbo >= (1 << 14) || a0 >= (1 << 14) || dch <= 0 || dch * N >= (1 << 14) || b0 * N >= (1 << 14)) { ok = false; return; }
+            pl.hm[npairs].a_off_lbo = (uint32_t)a0 | ((uint32_t)lbo << 16);
+            pl.hm[npairs].b_off_lbo = (uint32_t)(b0 * N) | ((uint32_t)(dch * N) << 16);
+            ++npairs;
+        };
+        for (int b = 0; b < nblk && ok; ++b)
+            for (int t = 0; t < 9 && ok; ++t) {
+                const int a_t = (int)blk[b].reg16 + (t / 3) * HW + (t % 3), b_t = blk[b].i0 + t * blk[b].np;
+                int q = 0;
+                for (; q + 1 < blk[b].np && ok; q += 2) add_pair(a_t + q * PLANE16, a_t + (q + 1) * PLANE16, b_t + q, b_t + q + 1);
+                if (q < blk[b].np) { singles[nsingle].a16 = a_t + q * PLANE16; singles[nsingle].bidx = b_t + q; ++nsingle; }
             }
+        for (int j = 0; j + 1 < nsingle && ok; j += 2) add_pair(singles[j].a16, singles[j + 1].a16, singles[j].bidx, singles[j + 1].bidx);
+        if (ok && (nsingle & 1)) {                                // odd chunk count: second half = any valid smem x the zero chunk at index nkc
+            if (!(a.nkc & 1)) ok = false;
+            else add_pair(singles[nsingle - 1].a16, singles[nsingle - 1].a16 + 1, singles[nsingle - 1].bidx, a.nkc);
         }
-        else ok = false;
+        if (nblk > tc::TMA_MAX_MAPS) ok = false;
         if (ok) {
             tp.bw_log = 3; tp.bh_log = 4;
-            tp.tiles_x = a.Wout >> 3; tp.tiles_y = a.Hout >> 4;
+            tp.tiles_x = a.Wout >> 3; tp.tiles_y = halo_ty;
             tp.ntiles = tp.tiles_x * tp.tiles_y * a.n;
             tp.mul_x = tc_magic(tp.tiles_x); tp.mul_y = tc_magic(tp.tiles_y);
             if ((unsigned long long)tp.ntiles * (unsigned)tp.tiles_x >= (1ull << 32)) ok = false;
@@ -566,7 +641,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             pl.a_slot_bytes = (int)(((size_t)reg16 * 16 + 1023) & ~(size_t)1023);
             tp.KS = 2; tp.nst = 0; tp.lag = 0;
             tp.resident_b = 1;
-            const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 + 256 * AYQ_MAX_OUT_ : 0;   // float2 sigmoid table + requant byte tables (MAGIC epilogue)
+            const size_t lut_bytes = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
             const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
             const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
             const size_t avail = (size_t)s.budget_kb * 1024 - fixed - w_bytes;
@@ -579,7 +654,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                 L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
                 if (N <= TC_CT_MAXN) {
                     for (int c = 0; c < N; ++c) {
-                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = magic ? -(L.et.k1[c] * AYQ_MAGIC_F) : h_tab[N + c];
+                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * ((magic || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
                         L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
                         L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
                     }
@@ -664,7 +739,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     }
     for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
     // shared memory budget
-    const size_t lut_bytes = a.epi == 0 ? (size_t)AYQ_LUT256 * 8 + 256 * AYQ_MAX_OUT_ : 0;   // float2 sigmoid table + requant byte tables (MAGIC epilogue)
+    const size_t lut_bytes = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
     const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = (size_t)s.budget_kb * 1024;
@@ -680,7 +755,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     if (N <= TC_CT_MAXN) {
         for (int c = 0; c < N; ++c) {
-            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] : h_tab[c]; L.et.i1[c] = magic ? -(L.et.k1[c] * AYQ_MAGIC_F) : h_tab[N + c];
+            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * ((magic || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
             L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
             L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
         }

@@ -116,6 +116,43 @@ __device__ __forceinline__ void fill_lut256_magic(float2* __restrict__ dst, cons
         dst[i] = make_float2(l, -__fmul_rn(l, AYQ_MAGIC_F));
     }
 }
+// MAGIC2: the variant the product kernels run.  Measured on B200 (tools/ubench, profiles/ubench_r2.txt): silu_magic above costs
+// 17.5 cycles per 32-element row per SM sub-partition however many warps run it, because F2I.S8 issues once every 8 cycles (two per
+// element = 16.5 cycles of the XU pipe) and the 8-byte table gather averages 3.5 shared-memory wavefronts.  Here
+//   * the first requant never becomes an integer: with the coefficient pre-scaled by 2^-8 (exact), y = RD_sat(t / 256 + (0.5 + 128) / 256)
+//     is (clamp(floor(t + 1/2), -128, 128) + 128) / 256 (the float floor cannot step over j / 256, all representable; .sat is
+//     the clamp), RD(y + 32768) has that index j in its low mantissa bits (ulp 2^-8), and ONE shift-add turns the bits into the
+//     shared-memory address of table entry j: no conversion, no separate clamp, no index arithmetic;
+//   * the table is replicated per lane (entry j of lane L at word j * 32 + L, 257 entries, 32.9 KB): every gather is one
+//     conflict-free wavefront of 4-byte words;
+//   * float(acc) = m - C is formed once (exact) and feeds both products as plain multiplies whose coefficient is a constant-bank
+//     operand (no per-channel constants in registers).
+// 11.5 issue slots per element with one XU instruction (the final saturating floor): bound by instruction issue.
+#define AYQ_LUTREP_N 257
+#define AYQ_LUTREP_BYTES (AYQ_LUTREP_N * 32 * 4)
+__device__ __forceinline__ void fill_lut_rep(float* __restrict__ dst, const float* __restrict__ table /*[2M+1]*/, int M, int tid, int nthreads) {
+    for (int i = tid; i < AYQ_LUTREP_N * 32; i += nthreads) {
+        const int r = max(-M, min(M, (i >> 5) - 128));
+        dst[i] = table[r + M];
+    }
+}
+// lut_thr = shared address of the table + 4 * lane + 0x80000000 (the bits of 32768.0f, shifted left by 7, wrap to 0x80000000)
+// WIDE: for layers whose accumulator bound exceeds 2^22 or whose clamp is not 127 (K = 6 / 4): float(acc) by conversion (one more
+// XU instruction) and explicit clamps to +-M on the result; everything else identical.
+template <bool WIDE>
+__device__ __forceinline__ int silu_magic2(int acc_plus_bias_magic, float k1s /* k1 * 2^-s1 * 2^-8 */, float k2p, uint32_t lut_thr, float half, int M = 127) {
+    const float af = WIDE ? __int2float_rn(acc_plus_bias_magic)                          // plain accumulator + bias
+                          : __fadd_rn(__int_as_float(acc_plus_bias_magic), -AYQ_MAGIC_F);  // exact: |acc + bias| < 2^22
+    const float t = __fmul_rn(k1s, af);                                                  // RN32(k1 * acc) * 2^-(s1 + 8), bit for bit
+    float y;
+    asm("add.rm.sat.f32 %0, %1, %2;" : "=f"(y) : "f"(t), "f"(0.501953125f));
+    const float w = __fadd_rd(y, 32768.0f);
+    float l;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(l) : "r"((__float_as_uint(w) << 7) + lut_thr));
+    const float pr = __fmul_rn(l, af);                                                   // RN32(sig * acc): res_silu *= res_conv_copy
+    const int r = floor_sat_s8(__fadd_rd(__fmul_rn(k2p, pr), half));
+    return WIDE ? max(-M, min(M, r)) : r;
+}
 // four values already in [-128, 127] -> one word (cvt.pack: two instructions instead of three logic ops)
 __device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d) {
     // cvt.pack d, x, y, z:  d = (z << 16) | (sat8(x) << 8) | sat8(y)

@@ -184,6 +184,8 @@ struct P1Args {
     const float* img;           // (n,3,H,W) fp32 (U8 == false)
     const uint8_t* img_u8;      // (n,3,H,W) uint8 (U8 == true): ToTensor (u8 / 255, stage_8_torch.py:985-990) happens in the kernel
     const float* amax;          // (n) per-image max|x|
+    float* amax_rw;             // same array, written by the fused abs-max step of conv_p1_tc_kernel<., true>
+    unsigned* sync;             // fused kernel: {ticket, band counter per image}, zeroed by the host
     const float* lut;           // sigmoid table [2M+1]
     int n, H, W, Hout, Wout, M;
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)

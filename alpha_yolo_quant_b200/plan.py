@@ -321,6 +321,9 @@ class PlanBuilder:
                                                out_bytes=sum(self.bufs[f[17 + 6 * i]][1] * self.bufs[f[17 + 6 * i]][2] * self.bufs[f[17 + 6 * i]][3]
                                                              * 16 * self.bufs[f[17 + 6 * i]][4] for i in range(f[16])
                                                              if not (f[17 + 6 * i + 5] == 2 and f[16] > 1)),
+                                               # SURVEY.md 8(d) figures, independent of layout / fusion choices: the reference conv's
+                                               # input read once and its output written once at 1 B per element
+                                               alg_in_bytes=cin * x.h * x.w, alg_out_bytes=cout * hout * wout,
                                                kmacs=cout * 16 * nkc * hout * wout))
         return results, new_scale
 

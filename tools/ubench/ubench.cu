@@ -20,6 +20,11 @@ struct Coef { float k1[16], c1[16], k2[16]; int bias[16]; };
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) epi_kernel(const __grid_constant__ Coef cf, int iters, int seed, unsigned* sink, long long* cyc) {
     __shared__ float2 lut2[256];
+    extern __shared__ __align__(128) float lut_rep[];
+    if (MODE == 7) {
+        for (int i = threadIdx.x; i < AYQ_LUTREP_N * 32; i += blockDim.x) lut_rep[i] = (float)((((i >> 5) * 3) & 127));
+    }
+    const uint32_t lut_thr = (uint32_t)__cvta_generic_to_shared(lut_rep) + ((threadIdx.x & 31u) << 2) + 0x80000000u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const float l = (float)(i < 128 ? (i * 3) & 127 : 127 - ((i * 5) & 63));
         lut2[i] = make_float2(l, -__fmul_rn(l, AYQ_MAGIC_F));
@@ -37,6 +42,7 @@ __global__ void __launch_bounds__(1024, 1) epi_kernel(const __grid_constant__ Co
         for (int j = 0; j < 16; ++j) {
             const int v = acc[j] + cf.bias[j];
             if (MODE == 0) r[j] = silu_magic(v, cf.k1[j], cf.c1[j], cf.k2[j], lut2, half);
+            else if (MODE == 7) r[j] = silu_magic2(v, cf.k1[j] * 0.00390625f, cf.k2[j], lut_thr, half);
             else if (MODE == 1) r[j] = floor_sat_s8(__int_as_float(v));
             else if (MODE == 2) r[j] = __float_as_int(__fadd_rd(__int_as_float(v), half));
             else if (MODE == 3) r[j] = __float_as_int(__fmaf_rn(cf.k1[j], __int_as_float(v), cf.c1[j]));
@@ -69,12 +75,14 @@ __global__ void __launch_bounds__(1024, 1) epi_kernel(const __grid_constant__ Co
 template <int MODE>
 static void run_epi(const char* name, int warps_per_smsp, const Coef& cf, unsigned* sink, long long* d_cyc) {
     const int threads = 128 * warps_per_smsp, iters = 2000;
-    epi_kernel<MODE><<<148, threads>>>(cf, 10, 1, sink, d_cyc);
+    const size_t dyn = MODE == 7 ? AYQ_LUTREP_BYTES : 0;
+    CK(cudaFuncSetAttribute(epi_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    epi_kernel<MODE><<<148, threads, dyn>>>(cf, 10, 1, sink, d_cyc);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    epi_kernel<MODE><<<148, threads>>>(cf, iters, 2, sink, d_cyc);
+    epi_kernel<MODE><<<148, threads, dyn>>>(cf, iters, 2, sink, d_cyc);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
@@ -105,12 +113,13 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 }
 __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int N, int iters, int nacc, long long* cyc) {
     extern __shared__ __align__(1024) unsigned char smem[];      // A: 8 K-steps x 4 KB, B: 8 x N*32
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (8 * 4096 + 8 * N * 32) / 4; i += 128) ((unsigned*)smem)[i] = 0x01010101u * (i & 3);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[0])), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[1])), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -125,26 +134,32 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int N, int iters, int 
     if (tid == 0) {
         const uint32_t idesc = make_idesc_i8(N);
         const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 8 * 4096);
-        uint32_t phase = 0;
+        // Two barriers used alternately, each with at most ONE phase outstanding: batch `it` commits to bars[it & 1]; before batch
+        // it + 1 is issued, batch it - 1 (the previous user of that barrier) is waited for.  Bounded spin: a protocol bug traps.
+        auto wait_bar = [&](int it) {
+            const uint32_t bar = smem_u32(&bars[it & 1]), parity = (uint32_t)(it >> 1) & 1u;
+            for (unsigned spin = 0;; ++spin) {
+                uint32_t done;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (done) break;
+                if (spin > (1u << 24)) __trap();
+            }
+        };
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) { ad[ks] = make_desc(a0 + ks * 4096, 2048, 128); bd[ks] = make_desc(b0 + ks * N * 32, N * 16, 128); }
+        const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)(nacc > 1 ? N : 0);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
-            for (int k = 0; k < 64; ++k) {
-                const int ks = k & 7;
-                mma_i8(tmem_base + (uint32_t)((k % nacc) * N), make_desc(a0 + ks * 4096, 2048, 128), make_desc(b0 + ks * N * 32, N * 16, 128), idesc, 1u);
+            for (int k8 = 0; k8 < 8; ++k8) {                       // 64 MMAs per batch; descriptors precomputed, no index arithmetic
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) mma_i8((ks & 1) ? d1 : d0, ad[ks], bd[ks], idesc, 1u);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
-            if (it >= 2) {                                   // keep at most three batches in flight
-                uint32_t done = 0;
-                while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
-                phase ^= 1;
-            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[it & 1])) : "memory");
+            if (it >= 1) wait_bar(it - 1);
         }
-        for (int w = 0; w < 2 && w < iters; ++w) {
-            uint32_t done = 0;
-            while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
-            phase ^= 1;
-        }
+        wait_bar(iters - 1);
         cyc[blockIdx.x] = clock64() - t0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -180,11 +195,13 @@ static void run_mma(int N, int nacc, long long* d_cyc) {
 }
 
 int main(int argc, char** argv) {
+    setvbuf(stdout, nullptr, _IONBF, 0);
     unsigned* sink; long long* d_cyc;
     CK(cudaMalloc(&sink, 4)); CK(cudaMalloc(&d_cyc, 148 * 8));
     Coef cf;
     for (int j = 0; j < 16; ++j) { cf.k1[j] = 0.0001f * (j + 3); cf.c1[j] = -cf.k1[j] * AYQ_MAGIC_F; cf.k2[j] = 0.00002f * (j + 5); cf.bias[j] = AYQ_MAGIC_I + 17 * j; }
     for (int w : {2, 4, 6, 8}) run_epi<0>("silu_magic (full)", w, cf, sink, d_cyc);
+    for (int w : {2, 4, 6, 8}) run_epi<7>("silu_magic2 (product)", w, cf, sink, d_cyc);
     for (int w : {4, 6}) run_epi<5>("silu_magic, no table", w, cf, sink, d_cyc);
     for (int w : {4, 6, 8}) run_epi<6>("silu, no XU (magic adds)", w, cf, sink, d_cyc);
     for (int w : {4, 8}) run_epi<1>("F2I.S8.FLOOR only", w, cf, sink, d_cyc);
