@@ -60,10 +60,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // wake-up of try_wait fires on unrelated barrier traffic of the CTA) and made up 11 % of ALL instructions the conv kernel
 // issued -- in a kernel whose epilogue is bound by instruction issue.  A producer is a whole ring ahead of the MMA warp, so it can
 // afford to look again only every ~0.5 us.
+template <int NS_SLEEP = 512>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t it = 0;; ++it) {
-        __nanosleep(512);
+        __nanosleep(NS_SLEEP);
         if (mbar_try_wait(bar, parity)) return;
         if (it > (1u << 23)) __trap();
     }
@@ -482,12 +483,20 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const Quad cf = CT ? quad_const(et, c0 + 4 * q) : quad_smem(tab_s, bias_s, N, c0 + 4 * q);
+        if (EPI == 0 && FAST >= 2) {                               // MAGIC2 / WIDE: two channels per packed-FP32 instruction
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const int v0 = acc[4 * q + j] + cf.b[j], v1 = acc[4 * q + j + 1] + cf.b[j + 1];   // FAST 2: b = bias + magic
+                acc[4 * q + j] = v0; acc[4 * q + j + 1] = v1;
+                silu_magic2_x2<FAST == 3>(v0, v1, f2_pack(cf.k1[j], cf.k1[j + 1]), f2_pack(cf.k2[j], cf.k2[j + 1]), lut_thr, M, r[4 * q + j], r[4 * q + j + 1]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
             acc[4 * q + j] = v;
-            if (EPI == 0 && FAST >= 2) r[4 * q + j] = silu_magic2<FAST == 3>(v, cf.k1[j], cf.k2[j], lut_thr, half, M);   // FAST 2: b = bias + magic; k1 = k1p * 2^-8
-            else if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
+            if (EPI == 0) r[4 * q + j] = FAST ? silu_q127f(v, cf.k1[j], cf.k2[j], lut_s, half)
                                               : silu_q(v, cf.k1[j], cf.i1[j], cf.k2[j], cf.i2[j], lut_s, M);
             else if (EPI == 1) r[4 * q + j] = FAST ? requant8_127f(__int2float_rn(v), cf.k1[j], half)
                                                    : requant8(__int2float_rn(v), cf.k1[j], cf.i1[j], M);

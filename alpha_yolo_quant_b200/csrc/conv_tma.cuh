@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 const TmaStage sg = pl.st[s];
                 const int gs = slot0 + slot;
                 const long long w0 = AYQ_CLK(a);
-                mbar_wait_relaxed(empty0 + 8 * gs, ephase);
+                mbar_wait_relaxed<768>(empty0 + 8 * gs, ephase);
                 if (AYQ_DBG(a)) d_wait += clock64() - w0;
                 if (elect_one()) {
                     const uint32_t bar = full0 + 8 * gs;
@@ -247,7 +247,9 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         long long d_we = 0, d_wf = 0, d_t0 = AYQ_CLK(a);
         for (int t = par < nq ? blockIdx.x + (m + 2 * par) * gridDim.x : tp.ntiles; t < tp.ntiles; t += 2 * nq * gridDim.x) {
             const long long w0 = AYQ_CLK(a);
-            mbar_wait(tempty0 + 8 * (TMA_NB * m + buf), ephase);
+            // When the epilogue is the bottleneck the issuers spend most of their time here, a whole accumulator ring ahead: a tight
+            // probe loop was 6 % of all issued instructions (ncu source view); look again every ~0.25 us instead.
+            mbar_wait_relaxed<256>(tempty0 + 8 * (TMA_NB * m + buf), ephase);
             if (AYQ_DBG(a)) d_we += clock64() - w0;
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)((m * nbuf + buf) * N);
@@ -545,8 +547,9 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     int nbuf = tma_csplit(N, a.epi) ? 2 : s.nbuf_mul * eg;        // accumulator ring per pipeline: two buffers per epilogue group ...
     while (nbuf > 1 && 2 * nbuf * N > 512) --nbuf;                // ... as far as the 512 TMEM columns go (cout 80: three, 256: one)
     if (nbuf > tc::TMA_NB) nbuf = tc::TMA_NB;
-    tp.nq = nbuf >= 2 && !getenv("AYQ_ONE_ISSUER") ? 2 : 1;       // two producer -> ring -> issuer chains per pipeline, each with private accumulators
-    if (tp.nq == 2) nbuf &= ~1;
+    // two producer -> ring -> issuer chains per pipeline when its accumulators split evenly between them (private even / odd
+    // buffers); an odd count (cout 80: three) keeps them all with a single chain -- measured faster than two chains with one each
+    tp.nq = nbuf >= 2 && (nbuf & 1) == 0 && !getenv("AYQ_ONE_ISSUER") ? 2 : 1;
     tp.nbuf = nbuf;
     while (cols < 2 * nbuf * N) cols <<= 1;                       // two pipelines x nbuf accumulators
     tp.tmem_cols = cols;
