@@ -310,6 +310,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
     CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
     CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
+    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
     CK(cudaFuncSetAttribute(nms_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nmsf_smem_bytes(h.n_anchors)));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
@@ -539,10 +541,12 @@ static bool p1_lean(ayq_engine* e, const int32_t* f, const PassArgs& pa) {
     const int* hb = (const int*)(e->host_data.data() + f[P1_BIAS_OFF]);
     long long sw[16];
     for (int co = 0; co < 16; ++co) { sw[co] = 0; for (int k = 0; k < 27; ++k) sw[co] += hw[co * 32 + k] < 0 ? -hw[co * 32 + k] : hw[co * 32 + k]; }
-    return M == 127 && f[P1_ACC_TAP] < 0 && H == 2 * Hout && W == 2 * Wout && Wout % P1_TW == 0 && Hout % P1_TH == 0 && W % 4 == 0 &&
+    bool range_ok = M <= 127;                                       // K != 8: explicit clamps, only the magic int -> float range has to hold
+    for (int co = 0; co < 16 && range_ok; ++co) range_ok = (hb[co] < 0 ? -(long long)hb[co] : (long long)hb[co]) + (long long)M * sw[co] < (1ll << 22) - 1;
+    return f[P1_ACC_TAP] < 0 && H == 2 * Hout && W == 2 * Wout && Wout % P1_TW == 0 && Hout % P1_TH == 0 && W % 4 == 0 &&
            (unsigned long long)n * Hout * Wout < (1ull << 28) &&
            (pa.img_u8 ? ((uintptr_t)pa.img_u8 & 15) == 0 || !pa.p1_fused && ((uintptr_t)pa.img_u8 & 3) == 0 : ((uintptr_t)pa.img & 15) == 0) &&
-           magic_coeffs_ok(16, M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw);
+           (M == 127 ? magic_coeffs_ok(16, M, ht, hb, (const float*)(e->host_data.data() + f[P1_LUT_OFF]), sw) : range_ok);
 }
 
 // launch plan op i of a pass
@@ -568,7 +572,13 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         a.ps = f[P1_OUT_PS];
         a.img0 = pa.p1_img0;
         const int nz = pa.p1_cnt >= 0 ? pa.p1_cnt : n;                // images of this launch (chunked abs-max -> Conv_P1 interleave)
-        const bool fold = a.M == 127;                              // K = 8: the kernel takes folded coefficients k * 2^-s (exact)
+        const bool lean = p1_lean(e, f, pa);
+#ifdef AYQ_TEST_BUILD
+        const bool lean_ok = lean && (f[P1_CLAMP] == 127 || (e->conv_impl >= 1 && !e->p1_dp4a));   // the CUDA-core cross-check kernel is K = 8 only
+#else
+        const bool lean_ok = lean;
+#endif
+        const bool fold = a.M == 127 || lean_ok;                   // folded coefficients k * 2^-s (exact): K = 8, and every lean launch
         P1Const pc;
         const int8_t* hw = (const int8_t*)(e->host_data.data() + f[P1_W_OFF]);         // [16][32], k = (ky*3+kx)*3 + c
         const float* ht = (const float*)(e->host_data.data() + f[P1_TAB_OFF]);         // [4][16]
@@ -582,10 +592,9 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
             pc.k1[co] = fold ? ht[co] * ht[16 + co] : ht[co]; pc.i1[co] = ht[16 + co];
             pc.k2[co] = fold ? ht[32 + co] * ht[48 + co] : ht[32 + co]; pc.i2[co] = ht[48 + co]; pc.bias[co] = hb[co];
         }
-        const bool lean = p1_lean(e, f, pa);
         a.amax_rw = amax;
         a.sync = (unsigned*)(amax + e->cap);
-        if (lean) {                                                // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
+        if (lean_ok) {                                             // MAGIC epilogue: accumulators start at bias + 0x4B400000, i1 = -k1p * C
             for (int co = 0; co < 16; ++co) { pc.i1[co] = -(pc.k1[co] * AYQ_MAGIC_F); pc.bias[co] = hb[co] + AYQ_MAGIC_I; }   // (i1: the test build's conv_p1_fast_kernel)
             P1Const pc2 = pc;                                      // tensor-core kernel: MAGIC2 epilogue, first coefficient pre-scaled by 2^-8
             for (int co = 0; co < 16; ++co) pc2.k1[co] = pc.k1[co] * 0.00390625f;
@@ -606,6 +615,10 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                     const unsigned nblk = (unsigned)(a.Hout / P1_TH) * (unsigned)(n + 1);
                     if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
                     else CK(launch_k(tc::conv_p1_tc_kernel<false, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                }
+                else if (a.M != 127) {                             // K = 6 / 4: explicit clamp to +-M
+                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                    else CK(launch_k(tc::conv_p1_tc_kernel<false, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
                 }
                 else if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
                 else CK(launch_k(tc::conv_p1_tc_kernel<false, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
@@ -703,7 +716,7 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     PassArgs pa{img, img_u8, n, dbox_cls, dets, counts};
     // fused abs-max + Conv_P1 (one read of the image from HBM instead of two): the lean tensor-core Conv_P1 of the product path
     pa.p1_fused = e->p1_fuse && !e->p1_dp4a && e->conv_impl >= 1 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1;
-    if (pa.p1_fused) pa.p1_fused = p1_lean(e, e->ops[0].f, pa);
+    if (pa.p1_fused) pa.p1_fused = e->ops[0].f[P1_CLAMP] == 127 && p1_lean(e, e->ops[0].f, pa);
     e->last_fused = pa.p1_fused;
     int pe = 0;
     if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));

@@ -175,7 +175,8 @@ struct P1B { int8_t b[2][4][16][16]; };    // [ox parity][ky2, zero, ky0, ky1][c
 // counter shows all nb bands.  A block only ever waits for blocks with SMALLER tickets, which have started and whose step (1)
 // depends on nothing, so the wait always ends (no co-residency assumption).  grid = nb * (n + 1) blocks; a.sync = {ticket,
 // band counters[n]} zeroed (with amax[]) by the host before the launch.
-template <bool U8, bool FUSED>
+// CLAMP: K != 8 (clamp 31 / 7): the same kernel with an explicit clamp of the SiLU result to +-M.
+template <bool U8, bool FUSED, bool CLAMP = false>
 __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_constant__ P1Args a, const __grid_constant__ P1Const pc,
                                                                 const __grid_constant__ P1B wb) {
     __shared__ __align__(1024) unsigned char sA[2][3][2048];      // [parity][ky2, ky0, ky1][128 rows][16 B]
@@ -368,7 +369,9 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
             int r[16];
             const uint32_t lut_thr = smem_u32(lut_rep) + ((uint32_t)(tid & 31) << 2) + 0x80000000u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = silu_magic2<false>(acc[j] + pc.bias[j], pc.k1[j], pc.k2[j], lut_thr, half);
+            for (int j = 0; j < 16; j += 2)
+                silu_magic2_x2<false, CLAMP>(acc[j] + pc.bias[j], acc[j + 1] + pc.bias[j + 1], f2_pack(pc.k1[j], pc.k1[j + 1]), f2_pack(pc.k2[j], pc.k2[j + 1]),
+                                             lut_thr, a.M, r[j], r[j + 1]);
             const int ox = x0 + 2 * h + e, oy = y0 + ty;
             const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
                                           (uint32_t)(oy >> 1) * (uint32_t)(a.Wout >> 1) + (uint32_t)(ox >> 1)
@@ -492,6 +495,14 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             }
             continue;
         }
+        if (EPI != 0 && FAST == 2) {                               // requantize-only epilogues, magic int -> float, two channels per instruction
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const int v0 = acc[4 * q + j] + cf.b[j], v1 = acc[4 * q + j + 1] + cf.b[j + 1];
+                requant_magic_x2<EPI == 2>(v0, v1, f2_pack(cf.k1[j], cf.k1[j + 1]), r[4 * q + j], r[4 * q + j + 1]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int v = acc[4 * q + j] + cf.b[j];
@@ -549,7 +560,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
         } else {
             uint32_t wd[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) wd[j] = (uint32_t)(r[2 * j] & 0xffff) | ((uint32_t)(r[2 * j + 1] & 0xffff) << 16);
+            for (int j = 0; j < 8; ++j) wd[j] = __byte_perm((uint32_t)r[2 * j], (uint32_t)r[2 * j + 1], 0x5410);   // low halves of two words
             uint4* dst = (uint4*)((int8_t*)a.out[0].base + 2u * off);
             dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);

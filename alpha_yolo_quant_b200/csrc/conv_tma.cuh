@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         if (FAST) {                                                 // folded coefficients: rows 0 / 2 hold k * 2^-s (exact)
             for (int i = tid; i < N; i += TMA_THREADS) {
                 const float k1p = __fmul_rn(a.tab[i], a.tab[N + i]);
-                tab_s[i] = FAST >= 2 ? __fmul_rn(k1p, 0.00390625f) : k1p;        // MAGIC2: coefficient of the first requant pre-scaled by 2^-8 (exact)
+                tab_s[i] = (EPI == 0 && FAST >= 2) ? __fmul_rn(k1p, 0.00390625f) : k1p;        // MAGIC2: coefficient of the first requant pre-scaled by 2^-8 (exact)
                 tab_s[2 * N + i] = __fmul_rn(a.tab[2 * N + i], a.tab[3 * N + i]);
                 tab_s[N + i] = 0.f; tab_s[3 * N + i] = 0.f;
             }
@@ -394,7 +394,7 @@ static inline TmaKernel tma_pick_t(int N, int epi) {
         default: return (N % 64 == 0) ? conv_tma_kernel<0, 0, FAST> : nullptr;   // column split: two groups x an even number of 16-channel groups
         }
     }
-    constexpr int F = FAST ? 1 : 0;                               // the magic / wide variants only exist for the SiLU epilogue
+    constexpr int F = FAST == 2 ? 2 : (FAST ? 1 : 0);             // requant epilogues: generic, folded, folded + magic int -> float
     if (epi == 1) return N == 64 ? conv_tma_kernel<4, 1, F> : (N % 64 == 0 ? conv_tma_kernel<0, 1, F> : nullptr);
     if (epi == 2) return N == 80 ? conv_tma_kernel<5, 2, F> : (N % 64 == 0 ? conv_tma_kernel<0, 2, F> : nullptr);
     return nullptr;
@@ -446,7 +446,7 @@ static inline bool magic_coeffs_ok(int N, int M, const float* h_tab, const int* 
     return true;
 }
 static inline bool magic_epilogue_ok(const ConvArgs& a, const float* h_tab, const int* h_bias, const float* h_lut, const int8_t* h_w, int nkc_pad) {
-    if (a.epi != 0 || !h_w || a.cout > 256) return false;
+    if (!h_w || a.cout > 256 || getenv("AYQ_NO_MAGIC")) return false;
     const int N = a.cout;
     long long sw[256];
     for (int c = 0; c < N; ++c) {
@@ -456,6 +456,11 @@ static inline bool magic_epilogue_ok(const ConvArgs& a, const float* h_tab, cons
             for (int j = 0; j < 16; ++j) t += w[j] < 0 ? -w[j] : w[j];
         }
         sw[c] = t;
+    }
+    if (a.epi != 0) {   // requantize-only epilogues (requant_last_layers / exponent_requant): only the magic int -> float range has to hold; inputs are K-bit activations (|x| <= 127)
+        for (int c = 0; c < N; ++c)
+            if ((h_bias[c] < 0 ? -(long long)h_bias[c] : (long long)h_bias[c]) + 127ll * sw[c] >= (1ll << 22) - 1) return false;
+        return a.epi == 2 || a.M == 127;
     }
     return magic_coeffs_ok(N, a.M, h_tab, h_bias, h_lut, sw);
 }
@@ -506,7 +511,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                       (unsigned long long)a.n * a.cout * a.Hout * a.Wout * (any_up ? 4 : 1) < (1ull << 32);
     const bool fast = magic || wide || tma_fast(a);               // FAST epilogue: folded coefficients k * 2^-s (exact), see fixedpoint.cuh
     L.fast = magic ? 2 : wide ? 3 : fast ? 1 : 0;
-    L.gen_outs = (magic || wide) && !tma_fast(a) ? 1 : 0;         // beyond "one identity output (+ phase-split copy)"
+    L.gen_outs = a.epi == 0 && (magic || wide) && !tma_fast(a) ? 1 : 0;         // beyond "one identity output (+ phase-split copy)"
     if (N % 16 != 0 || N < 16 || N > 256 || !tma_pick(N, a.epi, 0)) return 0;
     tc::TcParams& tp = L.tp;
     tp.role_hi = s.role_hi;
@@ -527,7 +532,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     const int slot_cap = N <= 64 ? 16 : 8;
     int slot_chunks = tp.nkc_pad < slot_cap ? tp.nkc_pad : slot_cap;
     {   // the ring needs at least four slots (two per pipeline): shrink the slot until they fit next to the tables / resident weights
-        const size_t lut_b = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;
+        const size_t lut_b = a.epi == 0 ? (((magic && a.epi == 0) || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;
         const size_t fixed_b = (size_t)N * 20 + lut_b + 64, w_b = (size_t)tp.nkc_pad * N * 16;
         const bool res = w_b <= (size_t)s.resident_kb * 1024;
         // ... and prefer eight (two per chain, so that a chain can load its next stage while the current one is multiplied) as long as
@@ -644,7 +649,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             pl.a_slot_bytes = (int)(((size_t)reg16 * 16 + 1023) & ~(size_t)1023);
             tp.KS = 2; tp.nst = 0; tp.lag = 0;
             tp.resident_b = 1;
-            const size_t lut_bytes = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
+            const size_t lut_bytes = a.epi == 0 ? (((magic && a.epi == 0) || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
             const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
             const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
             const size_t avail = (size_t)s.budget_kb * 1024 - fixed - w_bytes;
@@ -657,7 +662,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                 L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
                 if (N <= TC_CT_MAXN) {
                     for (int c = 0; c < N; ++c) {
-                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * ((magic || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
+                        L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * (((magic && a.epi == 0) || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
                         L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
                         L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
                     }
@@ -742,7 +747,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     }
     for (int q = nmaps; q < tc::TMA_MAX_MAPS; ++q) L.maps.m[q] = L.maps.m[0];
     // shared memory budget
-    const size_t lut_bytes = a.epi == 0 ? ((magic || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
+    const size_t lut_bytes = a.epi == 0 ? (((magic && a.epi == 0) || wide) ? (size_t)AYQ_LUTREP_BYTES : (size_t)AYQ_LUT256 * 8) + 256 * AYQ_MAX_OUT_ : 0;   // sigmoid table (MAGIC2: replicated per lane) + requant byte tables
     const size_t fixed = (size_t)N * 20 + lut_bytes + 64;
     const size_t w_bytes = (size_t)tp.nkc_pad * N * 16;
     const size_t budget = (size_t)s.budget_kb * 1024;
@@ -758,7 +763,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     L.grid = (unsigned)tp.ntiles < (unsigned)s.num_sms ? (unsigned)tp.ntiles : (unsigned)s.num_sms;
     if (N <= TC_CT_MAXN) {
         for (int c = 0; c < N; ++c) {
-            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * ((magic || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
+            L.et.k1[c] = fast ? h_tab[c] * h_tab[N + c] * (((magic && a.epi == 0) || wide) ? 0.00390625f : 1.f) : h_tab[c]; L.et.i1[c] = h_tab[N + c];   // MAGIC2: k1 * 2^-s1 * 2^-8
             L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
             L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
         }
