@@ -63,7 +63,7 @@ struct ayq_engine {
     uint8_t* d_img_u8[2] = {nullptr, nullptr};
     float* d_dets[2] = {nullptr, nullptr};
     int* d_counts[2] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_d2h[2]{};
+    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_d2h[2]{}, ev_img[2]{};   // ev_img: Conv_P1 (the last reader of the staged images) of the pass has run
     int host_cap = 0;
     bool host_u8 = false;
     long long host_passes = 0;             // passes the host pipeline has enqueued so far (slot = host_passes & 1; persists across async calls)
@@ -71,6 +71,7 @@ struct ayq_engine {
     // two calls on different streams (or a device entry followed by the host pipeline) never share the workspace concurrently
     cudaEvent_t ev_busy = nullptr;
     bool busy_recorded = false;
+    bool busy_from_host = false;           // ev_busy was recorded by the host pipeline itself (its streams need not wait for it)
     // profiling
     bool profiling = false;
     std::vector<float> op_ms;
@@ -104,6 +105,7 @@ static int wait_busy(ayq_engine* e, cudaStream_t st) {
 static int mark_busy(ayq_engine* e, cudaStream_t st) {
     CK(cudaEventRecord(e->ev_busy, st));
     e->busy_recorded = true;
+    e->busy_from_host = false;
     return 0;
 }
 static inline float f_from_bits(int32_t b) { float f; memcpy(&f, &b, 4); return f; }
@@ -392,6 +394,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
         if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
         if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+        if (e->ev_img[i]) cudaEventDestroy(e->ev_img[i]);
     }
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -529,7 +532,8 @@ static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
 #endif
 }
 
-struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; bool p1_fused = false; };
+struct PassArgs { const float* img; const uint8_t* img_u8; int n; float* dbox_cls; float* dets; int32_t* counts; int p1_img0 = 0; int p1_cnt = -1; bool p1_fused = false;
+                  cudaEvent_t ev_img = nullptr; };   // recorded right after Conv_P1, the last kernel that reads the input images
 
 // Conv_P1 takes the lean tensor-core kernel (conv_p1_tc_kernel, MAGIC epilogue) when K = 8, no accumulator tap is asked for, the
 // geometry is the 640 -> 320 one it is written for and the host can prove the epilogue's range conditions from the plan.
@@ -709,11 +713,13 @@ static void drop_graphs(ayq_engine* e) {
 // a given pass size they are captured once into a CUDA graph (with the PDL edges) and replayed; Conv_P1 / q_NMS carry the
 // caller's pointers and are launched directly.
 // img (fp32) or img_u8 (uint8, ToTensor fused into the abs-max and Conv_P1 kernels): exactly one is non-null
-static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st) {
+static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, cudaStream_t st,
+                    cudaEvent_t ev_img = nullptr) {
     const int H = e->hdr.img_h, W = e->hdr.img_w;
     float* amax = (float*)(e->ws + e->off_amax);
     const bool prof = e->profiling;
     PassArgs pa{img, img_u8, n, dbox_cls, dets, counts};
+    pa.ev_img = ev_img;
     // fused abs-max + Conv_P1 (one read of the image from HBM instead of two): the lean tensor-core Conv_P1 of the product path
     pa.p1_fused = e->p1_fuse && !e->p1_dp4a && e->conv_impl >= 1 && e->ops.size() && e->ops[0].f[0] == OP_CONV_P1;
     if (pa.p1_fused) pa.p1_fused = e->ops[0].f[P1_CLAMP] == 127 && p1_lean(e, e->ops[0].f, pa);
@@ -734,6 +740,7 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
             if (rc) return rc;
         }
         pa.p1_img0 = 0; pa.p1_cnt = -1;
+        if (pa.ev_img) CK(cudaEventRecord(pa.ev_img, st));
     } else if (pa.p1_fused) { /* the abs-max runs inside Conv_P1 */ }
     else if (img_u8) CK(launch_k(absmax_u8_kernel, dim3(32, n), dim3(256), 0, st, img_u8, amax, (size_t)3 * H * W));
     else CK(launch_k(absmax_kernel, dim3(64, n), dim3(256), 0, st, img, amax, (size_t)3 * H * W));
@@ -776,6 +783,7 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
         }
         int rc = launch_op(e, i, pa, st);
         if (rc) return rc;
+        if (pa.ev_img && e->ops[i].f[0] == OP_CONV_P1) CK(cudaEventRecord(pa.ev_img, st));   // the staging buffer of the images is free again
         if (prof) CK(cudaEventRecord(e->prof_ev[pe++], st));
         if (e->debug_sync) {
             cudaError_t de = cudaStreamSynchronize(st);
@@ -827,6 +835,7 @@ static int ensure_host_pipeline(ayq_engine* e, int m, bool u8) {
             CK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_img[i], cudaEventDisableTiming));
         }
     }
     if (m > e->host_cap || (u8 && !e->d_img_u8[0])) {
@@ -900,10 +909,10 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     if (rc) return rc;
     rc = ensure_host_pipeline(e, m_max, u8);
     if (rc) return rc;
-    if (e->busy_recorded) {                                        // a device-entry pass on a caller's stream may own the workspace
-        CK(cudaStreamWaitEvent(e->s_comp, e->ev_busy, 0));
-        CK(cudaStreamWaitEvent(e->s_copy, e->ev_busy, 0));
-    }
+    if (e->busy_recorded && !e->busy_from_host) {                  // a device-entry pass on a caller's stream may own the workspace
+        CK(cudaStreamWaitEvent(e->s_comp, e->ev_busy, 0));         // (after another host call the pipeline's own stream order and slot events
+        CK(cudaStreamWaitEvent(e->s_copy, e->ev_busy, 0));         //  suffice: making the copy stream wait for the previous call's last pass would
+    }                                                              //  serialise the upload of this call behind it)
     const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
     int i0 = 0;
     auto enqueue = [&]() -> int {
@@ -912,13 +921,13 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
             const int slot = (int)(e->host_passes & 1);
             const bool reuse = e->host_passes >= 2;
             // three streams: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i
-            if (reuse) CK(cudaStreamWaitEvent(e->s_copy, e->ev_done[slot], 0));   // d_img[slot] still being read
+            if (reuse) CK(cudaStreamWaitEvent(e->s_copy, e->ev_img[slot], 0));    // d_img[slot] is read by abs-max and Conv_P1 only: free long before the pass ends
             if (u8) CK(cudaMemcpyAsync(e->d_img_u8[slot], (const uint8_t*)img_host + (size_t)i0 * img_elems, img_elems * m, cudaMemcpyHostToDevice, e->s_copy));
             else CK(cudaMemcpyAsync(e->d_img[slot], (const float*)img_host + (size_t)i0 * img_elems, img_elems * m * sizeof(float), cudaMemcpyHostToDevice, e->s_copy));
             CK(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
             CK(cudaStreamWaitEvent(e->s_comp, e->ev_h2d[slot], 0));
             if (reuse) CK(cudaStreamWaitEvent(e->s_comp, e->ev_d2h[slot], 0));    // d_dets[slot] still draining
-            int prc = run_pass(e, u8 ? nullptr : e->d_img[slot], u8 ? e->d_img_u8[slot] : nullptr, m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp);
+            int prc = run_pass(e, u8 ? nullptr : e->d_img[slot], u8 ? e->d_img_u8[slot] : nullptr, m, nullptr, e->d_dets[slot], e->d_counts[slot], e->s_comp, e->ev_img[slot]);
             if (prc) return prc;
             CK(cudaEventRecord(e->ev_done[slot], e->s_comp));
             CK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[slot], 0));
@@ -938,6 +947,7 @@ static int forward_host_impl(ayq_engine* e, const void* img_host, bool u8, int n
     }
     CK(cudaEventRecord(e->ev_busy, e->s_comp));                    // later device-entry calls wait for the pipeline's last pass
     e->busy_recorded = true;
+    e->busy_from_host = true;
     return sync ? host_sync(e) : 0;
 }
 

@@ -31,6 +31,7 @@ OPS_IMG = 2 * 4371456000
 BYTES_IMG = 39993600                # fp32 image read + sum conv int8 inputs + outputs
 WORKLOAD = ('YOLOv8n full_quant + Detect head + q_NMS (stage_8_torch_full_quant path), K=8, 640x640, batch 256 per GPU '
             '(BASELINE configs[2]), random-init weights through the reference stage_2-7 pipeline')
+CONV_ALG_BYTES_IMG = 32211200       # sum over the 62 tcgen05 convs of input read + output written at 1 B / element
 
 
 def synth_batch_u8(n, seed0=0):
@@ -46,10 +47,18 @@ def synth_batch_u8(n, seed0=0):
 
 def load_peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    out = dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src='fallback')
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sus=d.get('bf16_tflops_sustained', d['bf16_tflops']), src='measured')
-    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src='fallback')
+        out = dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sus=d.get('bf16_tflops_sustained', d['bf16_tflops']), src='measured')
+    # dense int8 tcgen05 peak of this pool's B200 measured by tools/ubench/ubench.cu (kind::i8, M=128, N=256, K=32 from resident smem)
+    q = os.path.join(REPO, 'profiles', 'int8_peak_r2.json')
+    if os.path.exists(q):
+        j = json.load(open(q))
+        out.update(int8=j['int8_tops_dense'], int8_src=j['source'])
+    else:
+        out.update(int8=2 * out['bf16_sus'], int8_src='2 x sustained bf16 (no int8 probe committed)')
+    return out
 
 
 class ClockSampler:
@@ -178,6 +187,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--conv', default='tma', choices=['tma'], help='the product library has one convolution kernel family')
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU-baseline sample (images)')
+    ap.add_argument('--k', type=int, default=8, choices=[8, 6, 4], help='bit width of weights / activations (BASELINE configs[4]: 6 / 4)')
+    ap.add_argument('--sustain', type=float, default=0.0, help='additionally run the device-resident loop for this many seconds (clock record)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--ops-json', default=None, help='write the per-op time table here')
@@ -202,10 +213,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    K, sd, sc, ma = loaders.load_workload_npz(os.path.join(REPO, 'tests', 'golden', 'workload_k8.npz'))
+    K, sd, sc, ma = loaders.load_workload_npz(os.path.join(REPO, 'tests', 'golden', f'workload_k{args.k}.npz'))
     p = plan.compile_plan(sd, sc, ma, K)
-    e = engine.Engine(p, local, args.max_batch)
-    e.set_conv_impl(args.conv)
+    # product-level data-parallel entry (alpha_yolo_quant_b200/dataparallel.py): one engine per rank under torchrun
+    from alpha_yolo_quant_b200 import dataparallel as dpar
+    dpy = dpar.DataParallelYolo(p, devices=[local], max_batch=args.max_batch, group=dist.group.WORLD if dist is not None else None)
+    e = dpy.engines[0]
     B = args.batch
     u8 = synth_batch_u8(B, seed0=17 * rank)
     host_u8 = torch.from_numpy(u8).pin_memory()
@@ -240,39 +253,99 @@ def main():
     ms_max = float(t.item())
     value = B * world * args.steps / (ms_max / 1000.0)
     n_det = int(counts.sum().item())
-    if dist is not None:                              # results of all ranks in image order on rank 0 (outside the timed region)
-        from alpha_yolo_quant_b200 import dataparallel as dp
-        gd, gc = dp.gather_detections(dets, counts, B * world)
-        if rank == 0:
-            assert gd.shape[0] == B * world
-            n_det_global = int(gc.sum().item())
-
     # ---- end to end through the host-buffer C-ABI call
     e2e = None
+    e2e_f32 = None
     if not args.no_e2e:
-        dets_h = torch.empty((B, 300, 6), dtype=torch.float32).pin_memory()
-        counts_h = torch.empty((B,), dtype=torch.int32).pin_memory()
-        res = {}
+        # The call a user makes: DataParallelYolo / Engine.forward_host_async with pinned HOST buffers, one call per step, all K
+        # steps queued behind one another (each with its own result buffers) and ONE wait at the end, as a validation driver that
+        # streams batches would do (stage_8_torch.py:1004-1013 re-hosted).  Every step's H2D of the images and D2H of its detections
+        # are inside the timed region; consecutive steps overlap (upload of step i+1 under the kernels of step i), so only the first
+        # upload and the last pass of the whole run are exposed.  `sync_value` is the same with a blocking call per step.
+        NB = min(args.steps, 4)
+        dets_h = [torch.empty((B, 300, 6), dtype=torch.float32).pin_memory() for _ in range(NB)]
+        counts_h = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(NB)]
+        res, res_sync = {}, {}
         for name, src in (('f32', host_f32), ('u8', host_u8)):
             for _ in range(2):
-                e.forward_host(src, dets_h, counts_h)
+                e.forward_host(src, dets_h[0], counts_h[0])
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e.forward_host(src, dets_h, counts_h)       # synchronous: returns with results on the host
+            for i in range(args.steps):
+                e.forward_host_async(src, dets_h[i % NB], counts_h[i % NB])
+            e.wait()
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
             if dist is not None:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             res[name] = B * world * args.steps / float(tt.item())
-            assert int(counts_h.sum().item()) == n_det
+            for j in range(NB):
+                assert int(counts_h[j].sum().item()) == n_det
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                dpy.forward_shard(src, dets_h[0], counts_h[0])     # blocking per step: returns with the results on the host
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            res_sync[name] = B * world * args.steps / float(tt.item())
+            assert int(counts_h[0].sum().item()) == n_det
+        d2h = int(dets_h[0].numel() * 4 + counts_h[0].numel() * 4)
         # Headline: uint8 host images, the format the reference's validation loader holds before ToTensor
-        # (stage_8_torch.py:985-990, 1004-1013): H2D of the uint8 batch, ToTensor + forward + q_NMS on the GPU, D2H of the
-        # detections, all inside the timed C call.  The fp32-host-input variant (4x the PCIe bytes) is reported beside it.
-        e2e = {'value': res['u8'], 'unit': 'images/s', 'h2d_bytes_per_step': int(host_u8.numel()),
-               'd2h_bytes_per_step': int(dets_h.numel() * 4 + counts_h.numel() * 4),
-               'input': 'uint8 (B,3,640,640) pinned host -> ayq_forward_host_u8 (ToTensor on the GPU)',
-               'f32_input_value': res['f32'], 'f32_h2d_bytes_per_step': int(host_f32.numel() * 4)}
+        # (stage_8_torch.py:985-990): ToTensor + forward + q_NMS on the GPU.  `e2e_f32` is the reference's own forward() input
+        # format (fp32 (N,3,640,640), stage_8_torch_full_quant.py:704-710; 4x the PCIe bytes) measured the same way.
+        e2e = {'value': res['u8'], 'unit': 'images/s', 'h2d_bytes_per_step': int(host_u8.numel()), 'd2h_bytes_per_step': d2h,
+               'input': 'uint8 (B,3,640,640) pinned host -> ayq_forward_host_async x steps + ayq_wait (ToTensor on the GPU)',
+               'sync_value': res_sync['u8'], 'f32_input_value': res['f32'], 'f32_h2d_bytes_per_step': int(host_f32.numel() * 4)}
+        e2e_f32 = {'value': res['f32'], 'unit': 'images/s', 'h2d_bytes_per_step': int(host_f32.numel() * 4), 'd2h_bytes_per_step': d2h,
+                   'input': 'float32 (B,3,640,640) pinned host (the reference forward() input) -> ayq_forward_host_async x steps + ayq_wait',
+                   'sync_value': res_sync['f32']}
+        h2d_probe = os.path.join(REPO, 'profiles', 'h2d_probe_r2.json')
+        if os.path.exists(h2d_probe):                              # raw concurrent cudaMemcpyAsync H2D rate of this pool's box at N GPUs
+            hp = json.load(open(h2d_probe)).get(str(world))
+            if hp:
+                e2e['h2d_gbs'] = res['u8'] * host_u8[0].numel() / 1e9
+                e2e['h2d_probe_gbs'] = hp
+                e2e['frac_of_h2d_probe'] = e2e['h2d_gbs'] / hp
+                e2e_f32['h2d_gbs'] = res['f32'] * host_f32[0].numel() * 4 / 1e9
+                e2e_f32['frac_of_h2d_probe'] = e2e_f32['h2d_gbs'] / hp
+
+    # ---- every rank's detections equal the single-GPU result (rank 0 recomputes each rank's batch on its own GPU; outside timing)
+    parity = None
+    if dist is not None:
+        gd, gc = dpy.gather(dets.cpu(), counts.cpu(), B * world)
+        if rank == 0:
+            bad = 0
+            for r in range(world):
+                xr = (torch.from_numpy(synth_batch_u8(B, seed0=17 * r)).float() / 255.0).cuda()
+                dr, cr = e.forward(xr)
+                dr, cr = dr.cpu(), cr.cpu()
+                if not torch.equal(cr, gc[r * B:(r + 1) * B]):
+                    bad += 1
+                    continue
+                for i in range(B):
+                    k = int(cr[i])
+                    if not torch.equal(dr[i, :k], gd[r * B + i, :k]):
+                        bad += 1
+                        break
+            parity = {'ranks_checked': world, 'ranks_differing': bad, 'images': B * world,
+                      'check': 'rank 0 recomputed every rank\'s batch on GPU 0: counts and all detection rows bit-identical'}
+            assert bad == 0, parity
+
+    # ---- sustained run (clock record): the device-resident loop for >= args.sustain seconds
+    sustained = None
+    if args.sustain > 0 and rank == 0 and world == 1:
+        sampler2 = ClockSampler(local)
+        n_iter = max(int(args.sustain / (ms_max / args.steps / 1000.0)), 1)
+        evs0, evs1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs0.record(stream)
+        for _ in range(n_iter):
+            e.forward_into(x, dets, counts)
+        evs1.record(stream)
+        torch.cuda.synchronize()
+        ms_s = evs0.elapsed_time(evs1)
+        sustained = {'seconds': ms_s / 1000.0, 'steps': n_iter, 'value': B * n_iter / (ms_s / 1000.0), 'unit': 'images/s', 'clocks': sampler2.stop()}
 
     # ---- per-op device times (CUDA events around every kernel, outside the timed region) -> roofline of the dominant kernel
     roofline, top = None, None
@@ -297,8 +370,9 @@ def main():
             row = {'op': nm, 'avg_ms': float(avg_ms), 'share': float(op_ms[i] / op_ms.sum())}
             if meta:
                 out_b, in_b = meta['out_bytes'], meta['in_bytes']
-                row.update(macs_per_img=meta['macs'], bytes_per_img=in_b + out_b,
-                           tops=2e-9 * meta['macs'] * imgs / avg_ms, gbs=1e-6 * (in_b + out_b) * imgs / avg_ms)
+                alg = meta.get('alg_in_bytes', in_b) + meta.get('alg_out_bytes', out_b)    # independent of layout / fusion
+                row.update(macs_per_img=meta['macs'], bytes_per_img=alg, stored_bytes_per_img=in_b + out_b,
+                           tops=2e-9 * meta['macs'] * imgs / avg_ms, gbs=1e-6 * alg * imgs / avg_ms)
             rows.append(row)
         rows.sort(key=lambda r: -r['avg_ms'])
         top = rows[0]
@@ -309,22 +383,26 @@ def main():
         if conv_rows:
             imgs = min(B, args.max_batch)
             t_ms = sum(r['avg_ms'] for r in conv_rows)
-            byt = sum(r['bytes_per_img'] for r in conv_rows) * imgs
+            byt = sum(r['bytes_per_img'] for r in conv_rows) * imgs            # = 32,211,200 B per image x images
+            byt_stored = sum(r['stored_bytes_per_img'] for r in conv_rows) * imgs   # what this plan really moves (fused upsample copies, 2 B class logits)
+            if args.k == 8:
+                assert byt == CONV_ALG_BYTES_IMG * imgs, (byt, CONV_ALG_BYTES_IMG * imgs)
             mac = sum(r['macs_per_img'] for r in conv_rows) * imgs
             gbs = 1e-6 * byt / t_ms
-            kname = {'tcgen05': 'conv_tc_kernel', 'tma': 'conv_tma_kernel'}.get(args.conv, 'conv_dp4a_kernel')
-            traffic = None
-            tp_path = os.path.join(REPO, 'profiles', 'traffic_r1.json')
-            if args.conv == 'tma' and os.path.exists(tp_path):          # DRAM bytes per launch from the committed ncu --set full capture
+            traffic, traffic_src = None, None
+            tp_path = os.path.join(REPO, 'profiles', 'traffic_r2.json')
+            if os.path.exists(tp_path):     # DRAM bytes of all conv launches of one pass, ncu with caches left alone (--cache-control none)
                 tj = json.load(open(tp_path))
                 traffic = tj['dram_bytes_per_launch'] * imgs / tj['images_per_pass']
+                traffic_src = tj.get('source')
             roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
-                        'traffic': traffic, 'kernel': kname, 'launches_per_pass': len(conv_rows),
+                        'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'conv_tma_kernel', 'launches_per_pass': len(conv_rows),
                         'avg_launch_us': 1e3 * t_ms / len(conv_rows), 'algorithmic_bytes_per_launch': byt / len(conv_rows),
+                        'achieved_with_stored_bytes': 1e-6 * byt_stored / t_ms,
                         'share_of_pass': float(sum(r['share'] for r in conv_rows)), 'peak_source': peaks['src'],
-                        'tensor': {'achieved': 2e-9 * mac / t_ms, 'peak': 2 * peaks['bf16_sus'], 'unit': 'TOP/s int8 (peak = 2 x sustained bf16)',
-                                   'frac': 2e-9 * mac / t_ms / (2 * peaks['bf16_sus'])},
-                        'note': 'aggregate over all launches of the kernel in one pass: sum of algorithmic bytes / sum of event-timed durations'}
+                        'tensor': {'achieved': 2e-9 * mac / t_ms, 'peak': peaks['int8'], 'unit': 'TOP/s dense int8', 'peak_source': peaks['int8_src'],
+                                   'frac': 2e-9 * mac / t_ms / peaks['int8']},
+                        'note': 'aggregate over all launches of the kernel in one pass: sum of SURVEY 8(d) algorithmic bytes / sum of event-timed durations'}
         if args.ops_json:
             json.dump({'rows': rows, 'batch_per_pass': min(B, args.max_batch), 'conv': args.conv}, open(args.ops_json, 'w'), indent=1)
 
@@ -350,17 +428,17 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int8 weights/activations, int32 accumulate, fp32-rounded requant products', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD if B == 256 else WORKLOAD.replace('batch 256', f'batch {B}'),
+            'config': {'workload': (WORKLOAD if B == 256 else WORKLOAD.replace('batch 256', f'batch {B}')).replace('K=8', f'K={args.k}'),
                        'global_batch': B * world, 'images_per_pass': min(B, args.max_batch), 'conv_kernel': args.conv,
                        'l2': f'inputs larger than L2 ({B * 4915200 / 1e6:.0f} MB fp32 images per step, activations {e.workspace_bytes / 1e6:.0f} MB workspace)',
-                       'detections_per_step': n_det if dist is None else n_det_global},
-            'e2e': e2e, 'gpu_launches': int(e.launches_per_pass * passes * args.steps),
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+                       'detections_per_step': n_det},
+            'e2e': e2e, 'e2e_f32': e2e_f32, 'gpu_launches': int(e.launches_per_pass * passes * args.steps),
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'multi_gpu_parity': parity, 'sustained': sustained,
             'whole_net': {'hbm_frac': value / world * BYTES_IMG / 1e9 / peaks['hbm'], 'int8_tops': value / world * OPS_IMG / 1e12,
-                          'tensor_frac_vs_2x_bf16': value / world * OPS_IMG / 1e12 / (2 * peaks['bf16_sus']), 'peaks': peaks['src']},
+                          'tensor_frac': value / world * OPS_IMG / 1e12 / peaks['int8'], 'peaks': peaks['src'], 'int8_peak_source': peaks['int8_src']},
         }
         print(json.dumps(line))
-    e.close()
+    dpy.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
