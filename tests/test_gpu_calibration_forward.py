@@ -65,3 +65,30 @@ def test_all_64_taps_match_the_oracle_and_text_round_trip():
     parsed = G.parse_max_a_all(G.format_max_a_all(maxim_a))
     txt = G.format_max_a(parsed)
     assert txt.startswith('start: 1.0\n') and len(txt.splitlines()) == 64
+
+
+def test_all_64_taps_match_the_reference_run_and_timing(golden_dir, capsys):
+    """The reference's own fused weights (bnf_full_k8.npz) through the CUDA calibration forward: all 64 taps x 6 images against the
+    reference's max_a_all.txt (4 decimals in the text, fp32 summation order differs: rtol 2e-4), and the device time of the batch."""
+    from alpha_yolo_quant_b200 import calibration as G
+    full = np.load(os.path.join(golden_dir, 'bnf_full_k8.npz'))
+    head = np.load(os.path.join(golden_dir, 'bnf_head_k8.npz'))
+    ref = C.parse_max_a_all(str(head['max_a_all_txt']))
+    m = G.CalibrationModel({k: full[k] for k in full.files}, 'cuda')
+    x = torch.from_numpy(synth.to_input_array([synth.synth_image_u8(1000 + i) for i in range(synth.N_CALIB)])).cuda()
+    maxim_a = m.forward(x, {})
+    assert list(maxim_a) == [n for n, _ in ref] and len(maxim_a) == 64
+    for n, vals in ref:
+        np.testing.assert_allclose([float(v) for v in maxim_a[n]], vals, rtol=RTOL, atol=6e-5, err_msg=n)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xb = x.repeat(6, 1, 1, 1)[:32].contiguous()
+    m.forward(xb, {})
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        m.forward(xb, {})
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 3
+    with capsys.disabled():
+        print(f'\ncalibration forward (fp32 BN-fused network + 64 fused abs-max taps): {ms:.1f} ms per 32 images = {32 / ms * 1e3:.0f} images/s')

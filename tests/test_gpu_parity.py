@@ -410,3 +410,48 @@ def test_full_size_batch_matches_oracle_and_is_copy_invariant(golden_dir):
         if k:
             assert np.array_equal(dets[i, :k, :4], b) and np.array_equal(dets[i, :k, 4:6], c), (i, w)
     e.close()
+
+
+def test_batch_64_every_layer_matches_oracle(golden_dir):
+    """BASELINE configs[1]: batch 64 in ONE pass on the production plan, bit-exact per-layer integer activations.  The batch holds
+    eight shuffled copies of eight distinct images; every activation buffer the plan materialises (57 SiLU outputs where stored,
+    20 requantised tensors) must equal the oracle's tensor for the image at every one of the 64 positions."""
+    from alpha_yolo_quant_b200 import plan as P
+    p, e = _setup(golden_dir, 8, taps=False, impl='tma', max_batch=64)
+    wl = Y.Workload(os.path.join(golden_dir, 'workload_k8.npz'))
+    o = Y.OracleYolov8(wl)
+    seeds = [0, 1, 2, 5, 9, 10, 301, 302]
+    base = _images(seeds)
+    ref = o.forward(base.numpy(), trace=True)
+    tr = o.trace
+    rng = np.random.default_rng(5)
+    which = np.concatenate([rng.permutation(8) for _ in range(8)])
+    x = base[torch.from_numpy(which)].contiguous().cuda()
+    dets, counts = e.forward(x)
+    torch.cuda.synchronize()
+    _assert_all_convs_on_tma(p, e)
+    silu_names = [nm for nm, _ in P.LAYERS if not nm.endswith('_2') or not (nm.startswith('x_') and ('up_2' in nm or 'down_2' in nm))]
+    checked = 0
+    for idx, nm in enumerate(silu_names):
+        meta = p.info['layers'][nm]
+        buf = meta.get('silu_buf', meta.get('ps_buf'))
+        if buf is None:
+            continue
+        got = e.export_buffer(buf, 64).cpu().numpy()
+        assert np.array_equal(got, tr['silu'][idx][which]), nm
+        checked += 1
+    for t, (nm, j) in enumerate(REQUANT_ORDER):
+        bufs = p.info['layers'][nm].get('requant_bufs', [])
+        if j < len(bufs):
+            got = e.export_buffer(bufs[j][0], 64).cpu().numpy()
+            assert np.array_equal(got, tr['requant'][t][which]), (nm, j)
+            checked += 1
+    assert checked >= 60, checked
+    dets, counts = dets.cpu().numpy(), counts.cpu().numpy()
+    for i, w in enumerate(which):
+        b, c = ref[w]
+        k = int(counts[i])
+        assert k == (0 if b is None else b.shape[0]), (i, w)
+        if k:
+            assert np.array_equal(dets[i, :k, :4], b) and np.array_equal(dets[i, :k, 4:6], c), (i, w)
+    e.close()

@@ -125,3 +125,18 @@ def test_float_head_plan(golden_dir):
     hc = plan.header_constants(os.path.join(os.path.dirname(plan.__file__), 'csrc', 'plan_format.h'))
     assert hc['OP_HEAD_FLOAT'] == plan.OP_HEAD_FLOAT and hc['OP_NMS_FLOAT'] == plan.OP_NMS_FLOAT and hc['CF_ACC_BUF'] == 43
     assert hc['AYQ_PLAN_VERSION'] == plan.VERSION
+
+
+def test_algorithmic_bytes_equal_survey_8d(golden_dir):
+    """bench.py's roofline numerator: per conv, the reference conv's input read once + output written once at 1 B / element, independent
+    of this plan's layout choices (phase-split copies, duplicated addends, 2-byte class logits).  SURVEY.md 8(d): 19,980,800 +
+    15,097,600 B over the 63 convs; minus Conv_P1's share (1,228,800 + 1,638,400) = 32,211,200 B for the 62 tcgen05 convs."""
+    from alpha_yolo_quant_b200 import loaders, plan
+    K, sd, sc, ma = loaders.load_workload_npz(os.path.join(golden_dir, 'workload_k8.npz'))
+    p = plan.compile_plan(sd, sc, ma, K)
+    L = [v for v in p.info['layers'].values() if 'alg_in_bytes' in v]
+    assert len(L) == 62
+    assert sum(v['alg_in_bytes'] for v in L) == 19980800 - 1228800
+    assert sum(v['alg_out_bytes'] for v in L) == 15097600 - 1638400
+    assert sum(v['alg_in_bytes'] + v['alg_out_bytes'] for v in L) == 32211200
+    assert sum(v['macs'] for v in p.info['layers'].values() if 'macs' in v) == 4371456000

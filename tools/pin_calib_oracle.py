@@ -34,3 +34,6 @@ np.savez_compressed(os.path.join(REPO, 'tests', 'golden', 'bnf_head_k8.npz'),
                     **{f'{p}.{s}': sd[f'{p}.{s}'] for p in head for s in ('weight', 'bias')},
                     max_a_all_txt=np.array(txt), max_a_txt=np.array(open(os.path.join(res, 'max_a.txt')).read()))
 print('wrote tests/golden/bnf_head_k8.npz')
+# the FULL fused state_dict (127 tensors, 12 MB of fp32): pins all 64 taps in CI (tests/test_calibration_oracle.py) and on the GPU
+np.savez_compressed(os.path.join(REPO, 'tests', 'golden', 'bnf_full_k8.npz'), **{k: v for k, v in sd.items()})
+print('wrote tests/golden/bnf_full_k8.npz', os.path.getsize(os.path.join(REPO, 'tests', 'golden', 'bnf_full_k8.npz')), 'bytes')
