@@ -49,6 +49,8 @@ struct ayq_engine {
     unsigned char* ws = nullptr;
     size_t ws_bytes = 0;
     std::vector<size_t> buf_off;           // per buffer, for `cap`
+    bool guard = false;                    // AYQ_WS_GUARD=1: a 4 KB canary zone after every activation buffer (ayq_check_guards)
+    std::vector<size_t> guard_off;
     size_t off_amax = 0, off_dbox = 0, off_conf = 0, off_cls = 0, off_stage = 0;
     std::vector<KChunk*> d_kc;             // per op (device), rebuilt when cap changes
     std::vector<std::vector<KChunk>> h_kc; // per op (host copy)
@@ -95,6 +97,7 @@ struct ayq_engine {
     std::vector<std::vector<TmaSeg>> tma_segs;   // per op: source buffers of the conv input
 };
 
+#define AYQ_GUARD_BYTES 4096
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // The engine owns ONE workspace: entries on different streams are ordered through ev_busy (see ayq.h "stream semantics").
@@ -137,6 +140,7 @@ static int ensure_workspace(ayq_engine* e, int n) {
 }
 static int ensure_workspace_impl(ayq_engine* e, int n) {
     free_workspace(e);
+    e->guard_off.clear();
     const int cap = n;
     size_t off = 0;
     e->buf_off.resize(e->bufs.size());
@@ -144,6 +148,7 @@ static int ensure_workspace_impl(ayq_engine* e, int n) {
         const BufDesc& b = e->bufs[i];
         e->buf_off[i] = off;
         off = align_up(off + (size_t)b.nplanes * cap * b.H * b.W * 16 * b.elem_bytes, 1024);
+        if (e->guard) { e->guard_off.push_back(off); off += AYQ_GUARD_BYTES; }
     }
     const int A = e->hdr.n_anchors;
     e->off_amax = off; off = align_up(off + sizeof(float) * cap + sizeof(unsigned) * (cap + 1), 1024);   // amax[cap] | fused Conv_P1: ticket, band counters[cap]
@@ -152,6 +157,7 @@ static int ensure_workspace_impl(ayq_engine* e, int n) {
     e->off_cls = off;  off = align_up(off + sizeof(int) * (size_t)cap * A, 1024);
     CK(cudaMalloc(&e->ws, off));
     CK(cudaMemset(e->ws, 0, off));
+    for (size_t g : e->guard_off) CK(cudaMemset(e->ws + g, 0xA5, AYQ_GUARD_BYTES));
     e->ws_bytes = off;
     e->cap = cap;
     // resolve K-chunk tables and accumulator taps
@@ -308,12 +314,6 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 #endif
     CK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
-    CK(cudaFuncSetAttribute(tc::conv_p1_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AYQ_LUTREP_BYTES));
     CK(cudaFuncSetAttribute(nms_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nmsf_smem_bytes(h.n_anchors)));
     e->debug_sync = getenv("AYQ_DEBUG_SYNC") != nullptr;
     e->use_graph = getenv("AYQ_NO_GRAPH") == nullptr;
@@ -322,6 +322,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     if (e->role_prof) { return fail(-22, "AYQ_ROLE_PROF=1 needs the profiling build of the library (libayq_prof.so: python -m alpha_yolo_quant_b200.build --prof)"); }
 #endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
+    e->guard = getenv("AYQ_WS_GUARD") != nullptr;
     e->p1_fuse = getenv("AYQ_P1_FUSE") != nullptr;           // off: measured slower than the two kernels (843 vs 184 + 439 us per 256 images)
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_PASS")) e->host_pass = atoi(ev);
@@ -445,6 +446,21 @@ extern "C" int ayq_get_conv_impls(ayq_handle e, int32_t* impl, int cap) {
     for (int i = 0; i < n && i < cap; ++i)
         impl[i] = e->ops[i].f[0] == OP_CONV ? (i < (int)e->conv_impl_used.size() ? e->conv_impl_used[i] : -1) : -2;
     return n < cap ? n : cap;
+}
+// Own bounds check (compute-sanitizer is closed on the GPU pool this was developed on): with AYQ_WS_GUARD=1 every activation buffer
+// of the workspace is followed by a 4 KB canary zone; returns the number of canary bytes any kernel has overwritten (0 = clean).
+extern "C" int ayq_check_guards(ayq_handle e) {
+    if (!e) return fail(-22, "ayq_check_guards: null handle");
+    if (!e->guard) return fail(-22, "ayq_check_guards: create the engine with AYQ_WS_GUARD=1");
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> h(AYQ_GUARD_BYTES);
+    int bad = 0;
+    for (size_t g : e->guard_off) {
+        CK(cudaMemcpy(h.data(), e->ws + g, AYQ_GUARD_BYTES, cudaMemcpyDeviceToHost));
+        for (unsigned char c : h) bad += c != 0xA5;
+    }
+    return bad;
 }
 extern "C" int ayq_launches_per_pass(ayq_handle e) {
     if (!e) return fail(-22, "null handle");
@@ -617,15 +633,15 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                                 wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
                 if (pa.p1_fused) {                                 // abs-max inside the kernel, one image ahead (conv_tc.cuh): nb * (n + 1) tickets
                     const unsigned nblk = (unsigned)(a.Hout / P1_TH) * (unsigned)(n + 1);
-                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
-                    else CK(launch_k(tc::conv_p1_tc_kernel<false, true>, dim3(nblk), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, true>, dim3(nblk), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
+                    else CK(launch_k(tc::conv_p1_tc_kernel<false, true>, dim3(nblk), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
                 }
                 else if (a.M != 127) {                             // K = 6 / 4: explicit clamp to +-M
-                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
-                    else CK(launch_k(tc::conv_p1_tc_kernel<false, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                    if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
+                    else CK(launch_k(tc::conv_p1_tc_kernel<false, false, true>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
                 }
-                else if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
-                else CK(launch_k(tc::conv_p1_tc_kernel<false, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), AYQ_LUTREP_BYTES, st, a, pc2, wb));
+                else if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
+                else CK(launch_k(tc::conv_p1_tc_kernel<false, false>, dim3(1, a.Hout / P1_TH, nz), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
             }
 #ifdef AYQ_TEST_BUILD
             else if (pa.img_u8) CK(launch_k(conv_p1_fast_kernel<true>, dim3(1, a.Hout / P1_TH, nz), dim3(256), 0, st, a, pc));

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
     __shared__ __align__(1024) unsigned char sA[2][3][2048];      // [parity][ky2, ky0, ky1][128 rows][16 B]
     __shared__ __align__(128) unsigned char sB[2][4][256];
     __shared__ __align__(16) unsigned sQ[2 * P1_TH + 1][56];       // 224-byte rows (conflict-free word stride 3 across a half warp)
-    extern __shared__ __align__(128) float lut_rep[];             // per-lane replicated sigmoid table (AYQ_LUTREP_BYTES of dynamic smem)
+    __shared__ __align__(128) float lut_rep[AYQ_LUTREP_N * 8];     // sigmoid table, eight copies per entry (8 KB: occupancy matters more here than the last bank conflict)
     __shared__ unsigned qlut[U8 ? 256 : 1];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
         if (ia == 0) return;                                      // no image -1 to convolve (nothing allocated yet: plain exit)
         img = ia - 1; y0 = band * P1_TH;
     }
-    fill_lut_rep(lut_rep, a.lut, a.M, tid, P1TC_THREADS);
+    fill_lut_rep<3>(lut_rep, a.lut, a.M, tid, P1TC_THREADS);
     if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];
     if (tid == 0) {
         mbar_init(smem_u32(&bar), 1);
@@ -367,10 +367,10 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
             tmem_ld_wait16(acc);
             const float half = a.half;
             int r[16];
-            const uint32_t lut_thr = smem_u32(lut_rep) + ((uint32_t)(tid & 31) << 2) + 0x80000000u;
+            const uint32_t lut_thr = lut_rep_thread_base<3>(smem_u32(lut_rep), (uint32_t)tid & 31u);
 #pragma unroll
             for (int j = 0; j < 16; j += 2)
-                silu_magic2_x2<false, CLAMP>(acc[j] + pc.bias[j], acc[j + 1] + pc.bias[j + 1], f2_pack(pc.k1[j], pc.k1[j + 1]), f2_pack(pc.k2[j], pc.k2[j + 1]),
+                silu_magic2_x2<false, CLAMP, 3>(acc[j] + pc.bias[j], acc[j + 1] + pc.bias[j + 1], f2_pack(pc.k1[j], pc.k1[j + 1]), f2_pack(pc.k2[j], pc.k2[j + 1]),
                                              lut_thr, a.M, r[j], r[j + 1]);
             const int ox = x0 + 2 * h + e, oy = y0 + ty;
             const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
@@ -481,7 +481,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
                                              const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u, 0u}) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
-    const uint32_t lut_thr = smem_u32(lut_s) + ((threadIdx.x & 31u) << 2) + 0x80000000u;     // MAGIC2 (loop invariant, hoisted by the compiler)
+    const uint32_t lut_thr = lut_rep_thread_base<5>(smem_u32(lut_s), threadIdx.x & 31u);     // MAGIC2 (loop invariant, hoisted by the compiler)
     int r[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

@@ -130,11 +130,20 @@ __device__ __forceinline__ void fill_lut256_magic(float2* __restrict__ dst, cons
 // 11.5 issue slots per element with one XU instruction (the final saturating floor): bound by instruction issue.
 #define AYQ_LUTREP_N 257
 #define AYQ_LUTREP_BYTES (AYQ_LUTREP_N * 32 * 4)
+// REP_LOG: log2 of the copies per entry (5 = one per lane, conflict-free; 3 = eight copies, 8 KB, at most 4-way conflicts: for
+// kernels that are not bound by the gather and need the shared memory for occupancy, i.e. Conv_P1)
+#define AYQ_LUTREP8_BYTES (AYQ_LUTREP_N * 8 * 4)
+template <int REP_LOG = 5>
 __device__ __forceinline__ void fill_lut_rep(float* __restrict__ dst, const float* __restrict__ table /*[2M+1]*/, int M, int tid, int nthreads) {
-    for (int i = tid; i < AYQ_LUTREP_N * 32; i += nthreads) {
-        const int r = max(-M, min(M, (i >> 5) - 128));
+    for (int i = tid; i < (AYQ_LUTREP_N << REP_LOG); i += nthreads) {
+        const int r = max(-M, min(M, (i >> REP_LOG) - 128));
         dst[i] = table[r + M];
     }
+}
+// per-thread part of the gather address: table base + 4 * (lane mod copies) + the wrapped bits of 32768.0f << (2 + REP_LOG)
+template <int REP_LOG = 5>
+__device__ __forceinline__ uint32_t lut_rep_thread_base(uint32_t table_smem_addr, uint32_t lane) {
+    return table_smem_addr + ((lane & ((1u << REP_LOG) - 1u)) << 2) - (0x47000000u << (2 + REP_LOG));
 }
 // lut_thr = shared address of the table + 4 * lane + 0x80000000 (the bits of 32768.0f, shifted left by 7, wrap to 0x80000000)
 // WIDE: for layers whose accumulator bound exceeds 2^22 or whose clamp is not 127 (K = 6 / 4): float(acc) by conversion (one more
@@ -166,7 +175,7 @@ __device__ __forceinline__ f32x2_t f2_mul_rn(f32x2_t a, f32x2_t b) { f32x2_t r; 
 // silu_magic2 on elements (v0, v1) of two adjacent channels; k1s / k2p hold the two channels' coefficients
 // I2F: float(acc) by conversion (accumulators beyond 2^22) instead of the magic add; CLAMP: explicit clamp of the result to +-M
 // (a clamp other than 127, or a layer for which the host cannot prove that -128 is unreachable)
-template <bool I2F, bool CLAMP = I2F>
+template <bool I2F, bool CLAMP = I2F, int REP_LOG = 5>
 __device__ __forceinline__ void silu_magic2_x2(int v0, int v1, f32x2_t k1s, f32x2_t k2p, uint32_t lut_thr, int M, int& r0, int& r1) {
     const f32x2_t af = I2F ? f2_pack(__int2float_rn(v0), __int2float_rn(v1))
                             : f2_add_rn(f2_pack(__int_as_float(v0), __int_as_float(v1)), f2_pack(-AYQ_MAGIC_F, -AYQ_MAGIC_F));
@@ -175,8 +184,8 @@ __device__ __forceinline__ void silu_magic2_x2(int v0, int v1, f32x2_t k1s, f32x
     asm("add.rm.sat.f32 %0, %1, %2;" : "=f"(y0) : "f"(t0), "f"(0.501953125f));
     asm("add.rm.sat.f32 %0, %1, %2;" : "=f"(y1) : "f"(t1), "f"(0.501953125f));
     f2_unpack(f2_add_rm(f2_pack(y0, y1), f2_pack(32768.0f, 32768.0f)), w0, w1);
-    asm("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"((__float_as_uint(w0) << 7) + lut_thr));
-    asm("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"((__float_as_uint(w1) << 7) + lut_thr));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"((__float_as_uint(w0) << (2 + REP_LOG)) + lut_thr));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"((__float_as_uint(w1) << (2 + REP_LOG)) + lut_thr));
     const f32x2_t pr = f2_mul_rn(f2_pack(l0, l1), af);
     f2_unpack(f2_add_rm(f2_mul_rn(k2p, pr), f2_pack(0.5f, 0.5f)), z0, z1);
     r0 = floor_sat_s8(z0); r1 = floor_sat_s8(z1);

@@ -33,6 +33,7 @@ SIGNATURES = {
     'ayq_forward_host_async': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
     'ayq_wait': (_int, [_vp]),
     'ayq_get_conv_impls': (_int, [_vp, _vp, _int]),
+    'ayq_check_guards': (_int, [_vp]),
     'ayq_export_buffer': (_int, [_vp, _int, _int, _vp, _vp]),
     'ayq_buffer_shape': (_int, [_vp, _int, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_int)]),
     'ayq_export_acc_tap': (_int, [_vp, _int, _int, _vp, _vp]),
@@ -179,6 +180,10 @@ class Engine:
     def wait(self):
         """Block until every queued forward_host_async call has delivered its results."""
         self._ck(self.lib.ayq_wait(self._h))
+
+    def check_guards(self):
+        """Canary bytes overwritten behind the activation buffers (needs AYQ_WS_GUARD=1 at engine creation); 0 = clean."""
+        return self._ck(self.lib.ayq_check_guards(self._h))
 
     def conv_impls(self):
         """Per plan op: 2 / 1 / 0 = the conv kernel family that ran it in the last pass (2 = TMA-fed tcgen05), -2 = not a conv."""

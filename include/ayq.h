@@ -78,6 +78,10 @@ int ayq_export_buffer(ayq_handle h, int buf, int n, int32_t* dst, void* stream);
 int ayq_buffer_shape(ayq_handle h, int buf, int* channels, int* height, int* width);
 /* raw int32 conv accumulators (n, cout, H, W) of the last pass; only for plans compiled with taps */
 int ayq_export_acc_tap(ayq_handle h, int tap, int n, int32_t* dst, void* stream);
+/* Own out-of-bounds check for the activation workspace: when the engine is created with AYQ_WS_GUARD=1 in the environment, a 4 KB
+ * canary zone follows every activation buffer; returns how many canary bytes have been overwritten so far (0 = no kernel wrote past
+ * the end of a buffer), or a negative error. */
+int ayq_check_guards(ayq_handle h);
 /* number of kernels one internal pass launches (bench.py gpu_launches) */
 int ayq_launches_per_pass(ayq_handle h);
 /* Convolution kernel family: 2 = TMA-fed tcgen05 / TMEM implicit GEMM (conv_tma_kernel) -- the ONLY family in the product

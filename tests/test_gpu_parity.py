@@ -455,3 +455,16 @@ def test_batch_64_every_layer_matches_oracle(golden_dir):
         if k:
             assert np.array_equal(dets[i, :k, :4], b) and np.array_equal(dets[i, :k, 4:6], c), (i, w)
     e.close()
+
+
+def test_no_kernel_writes_past_its_activation_buffers(golden_dir, monkeypatch):
+    """Own bounds check (compute-sanitizer is closed on this GPU pool): 4 KB canary zones behind every activation buffer stay intact
+    after ragged passes of every epilogue variant -- K = 8 production (MAGIC2 / FAST, halo with overhanging tiles on the 40 x 40
+    maps), K = 8 with accumulator taps (generic), K = 6 and K = 4 (WIDE)."""
+    monkeypatch.setenv('AYQ_WS_GUARD', '1')
+    for k, taps, n in ((8, False, 5), (8, True, 3), (6, False, 3), (4, False, 2)):
+        p, e = _setup(golden_dir, k, taps=taps, impl='tma', max_batch=4)
+        dets, counts = e.forward(_images(range(n)).cuda())          # n > max_batch for the first: a full and a ragged pass
+        torch.cuda.synchronize()
+        assert e.check_guards() == 0, (k, taps)
+        e.close()
