@@ -632,7 +632,8 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
                             for (int t = 0; t < 9; ++t)            // t = kx * 3 + c
                                 wb.b[par][ky == 2 ? 0 : ky + 2][co][(par ? 3 : 1) + t] = hw[co * 32 + ky * 9 + t];
                 if (pa.p1_fused) {                                 // abs-max inside the kernel, one image ahead (conv_tc.cuh): nb * (n + 1) tickets
-                    const unsigned nblk = (unsigned)(a.Hout / P1_TH) * (unsigned)(n + 1);
+                    a.fuse_d = getenv("AYQ_P1_FUSE_D") ? atoi(getenv("AYQ_P1_FUSE_D")) : 0;
+                    const unsigned nblk = (unsigned)(a.Hout / P1_TH) * (unsigned)(n + a.fuse_d);
                     if (pa.img_u8) CK(launch_k(tc::conv_p1_tc_kernel<true, true>, dim3(nblk), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
                     else CK(launch_k(tc::conv_p1_tc_kernel<false, true>, dim3(nblk), dim3(P1TC_THREADS), 0, st, a, pc2, wb));
                 }
@@ -666,7 +667,8 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         const int8_t* in = (const int8_t*)(e->ws + e->buf_off[f[PL_IN_BUF]]) + (size_t)f[PL_IN_PLANE0] * ppx;
         int8_t* out = (int8_t*)(e->ws + e->buf_off[f[PL_OUT_BUF]]) + (size_t)f[PL_OUT_PLANE0] * ppx;
         (void)ib; (void)ob;
-        CK(launch_k(sppf_pool_kernel, dim3(f[PL_NPLANES], n), dim3(256), (size_t)f[PL_H] * f[PL_W] * 16 * 2, st, in, out, n, (int)f[PL_H], (int)f[PL_W], (int)f[PL_NPLANES]));
+        if (f[PL_H] * f[PL_W] > 1024) return fail(-38, "SPPF pool: %dx%d map (one thread per pixel, at most 1024)", f[PL_H], f[PL_W]);
+        CK(launch_k(sppf_pool_kernel, dim3(f[PL_NPLANES], n), dim3((unsigned)((f[PL_H] * f[PL_W] + 31) & ~31)), (size_t)f[PL_H] * f[PL_W] * 16 * 2, st, in, out, n, (int)f[PL_H], (int)f[PL_W], (int)f[PL_NPLANES]));
         break;
     }
     case OP_HEAD: {

@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
                 atomicAdd(a.sync + 1 + ia, 1u);
             }
         }
-        if (ia == 0) return;                                      // no image -1 to convolve (nothing allocated yet: plain exit)
-        img = ia - 1; y0 = band * P1_TH;
+        // a.fuse_d = 1: convolve the image whose abs-max the PREVIOUS nb tickets published (only smaller tickets are waited for);
+        // a.fuse_d = 0: convolve the same image (its nb blocks hold consecutive tickets and are resident together: needs at least nb
+        // block slots on the device, which the host checks), so the band is re-read while it is still in this SM's reach
+        if (ia < a.fuse_d || ia - a.fuse_d >= a.n) return;        // nothing to convolve for this ticket (nothing allocated yet: plain exit)
+        img = ia - a.fuse_d; y0 = band * P1_TH;
     }
     fill_lut_rep<3>(lut_rep, a.lut, a.M, tid, P1TC_THREADS);
     if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];

@@ -186,6 +186,7 @@ struct P1Args {
     const float* amax;          // (n) per-image max|x|
     float* amax_rw;             // same array, written by the fused abs-max step of conv_p1_tc_kernel<., true>
     unsigned* sync;             // fused kernel: {ticket, band counter per image}, zeroed by the host
+    int fuse_d;                 // fused kernel: images between the abs-max step and the convolution step of a ticket (0 or 1)
     const float* lut;           // sigmoid table [2M+1]
     int n, H, W, Hout, Wout, M;
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
@@ -451,42 +452,42 @@ __global__ void __launch_bounds__(256) absmax_u8_kernel(const uint8_t* __restric
 
 // ---- SPPF: three cascaded 5x5 stride-1 max pools (padding = -inf, i.e. window clipped to the map) -----
 // grid (nplanes, n), block 256.  in/out: plane buffers (plane, n, H, W, 16) int8.
-__global__ void __launch_bounds__(256) sppf_pool_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out,
-                                                        int n, int H, int W, int nplanes) {
+__device__ __forceinline__ uint4 vmaxs4x4(uint4 a, uint4 b) { return make_uint4(__vmaxs4(a.x, b.x), __vmaxs4(a.y, b.y), __vmaxs4(a.z, b.z), __vmaxs4(a.w, b.w)); }
+// block = H * W threads rounded up to a warp (<= 1024): thread = pixel (its x, y are computed once), 16 channels = one uint4.
+__global__ void __launch_bounds__(1024) sppf_pool_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out,
+                                                         int n, int H, int W, int nplanes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* A = (unsigned*)smem_raw;                  // [H*W*4]
-    unsigned* B = A + H * W * 4;
+    uint4* A = (uint4*)smem_raw;                        // [H*W]
+    uint4* B = A + H * W;
     const int pl = blockIdx.x, img = blockIdx.y;
     pdl_trigger();
     pdl_wait();
     const size_t plane_px = (size_t)n * H * W;
-    const unsigned* src = (const unsigned*)(in + ((size_t)pl * plane_px + (size_t)img * H * W) * 16);
-    const int nw = H * W * 4;
-    for (int i = threadIdx.x; i < nw; i += 256) A[i] = src[i];
+    const int px = threadIdx.x, npx = H * W;
+    const bool act = px < npx;
+    const int y = px / W, x = px - y * W;
+    const uint4* src = (const uint4*)(in + ((size_t)pl * plane_px + (size_t)img * npx) * 16);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (act) { v = src[px]; A[px] = v; }
     __syncthreads();
     for (int stage = 0; stage < 3; ++stage) {
-        for (int i = threadIdx.x; i < nw; i += 256) {   // row pass: max over x-2..x+2
-            const int wq = i & 3, px = i >> 2, x = px % W, y = px / W;
-            unsigned m = A[i];
+        if (act) {                                      // row pass: max over x-2..x+2 (window clipped to the map = -inf padding)
+            uint4 m = v;
 #pragma unroll
-            for (int d = -2; d <= 2; ++d) {
-                const int xx = x + d;
-                if (d != 0 && xx >= 0 && xx < W) m = __vmaxs4(m, A[((y * W + xx) << 2) + wq]);
-            }
-            B[i] = m;
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && x + d >= 0 && x + d < W) m = vmaxs4x4(m, A[px + d]);
+            B[px] = m;
+            v = m;
         }
         __syncthreads();
-        unsigned* dst = (unsigned*)(out + ((size_t)(stage * nplanes + pl) * plane_px + (size_t)img * H * W) * 16);
-        for (int i = threadIdx.x; i < nw; i += 256) {   // column pass
-            const int wq = i & 3, px = i >> 2, x = px % W, y = px / W;
-            unsigned m = B[i];
+        if (act) {                                      // column pass
+            uint4 m = v;
 #pragma unroll
-            for (int d = -2; d <= 2; ++d) {
-                const int yy = y + d;
-                if (d != 0 && yy >= 0 && yy < H) m = __vmaxs4(m, B[((yy * W + x) << 2) + wq]);
-            }
-            A[i] = m;
-            dst[i] = m;
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && y + d >= 0 && y + d < H) m = vmaxs4x4(m, B[px + d * W]);
+            A[px] = m;
+            v = m;
+            ((uint4*)(out + ((size_t)(stage * nplanes + pl) * plane_px + (size_t)img * npx) * 16))[px] = m;
         }
         __syncthreads();
     }
