@@ -371,10 +371,11 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
             const float half = a.half;
             int r[16];
             const uint32_t lut_thr = lut_rep_thread_base<3>(smem_u32(lut_rep), (uint32_t)tid & 31u);
+            const EpiPairs cp = epi_pairs();
 #pragma unroll
             for (int j = 0; j < 16; j += 2)
                 silu_magic2_x2<false, CLAMP, 3>(acc[j] + pc.bias[j], acc[j + 1] + pc.bias[j + 1], f2_pack(pc.k1[j], pc.k1[j + 1]), f2_pack(pc.k2[j], pc.k2[j + 1]),
-                                             lut_thr, a.M, r[j], r[j + 1]);
+                                             lut_thr, a.M, r[j], r[j + 1], cp);
             const int ox = x0 + 2 * h + e, oy = y0 + ty;
             const uint32_t p = a.ps ? ((uint32_t)(((oy & 1) << 1) | (ox & 1)) * (uint32_t)a.n + (uint32_t)img) * (uint32_t)((a.Hout >> 1) * (a.Wout >> 1)) +
                                           (uint32_t)(oy >> 1) * (uint32_t)(a.Wout >> 1) + (uint32_t)(ox >> 1)
@@ -436,13 +437,20 @@ __device__ __forceinline__ TileCoord tile_coord(int t, const TcParams& tp) {
 // Per-channel epilogue coefficients for cout <= 80, passed as a __grid_constant__ kernel parameter: with the channel
 // loop fully unrolled every coefficient is a constant-bank / uniform-register operand (no loads in the inner loop).
 #define TC_CT_MAXN 80
-struct EpiTab { float k1[TC_CT_MAXN], i1[TC_CT_MAXN], k2[TC_CT_MAXN], i2[TC_CT_MAXN]; int bias[TC_CT_MAXN]; };
+// 16-byte aligned in the parameter space: the packed epilogue takes coefficient PAIRS (k1[c], k1[c+1]) as 64-bit uniform operands;
+// unaligned, every pair cost a UMOV shuffle (37 per 32 elements in the ncu source view).
+// k1x2 / k2x2: the same k1 / k2 as 64-bit PAIRS (channels 2i, 2i+1), the operand form of the packed FP32x2 epilogue -- as a 64-bit
+// array the compiler fetches them with aligned LDCU.64 / .128 straight into the uniform-register pair (building the pair from
+// two floats cost a UMOV shuffle per pair: 37 per 32 elements in the ncu source view).
+struct alignas(16) EpiTab { float k1[TC_CT_MAXN], i1[TC_CT_MAXN], k2[TC_CT_MAXN], i2[TC_CT_MAXN]; int bias[TC_CT_MAXN];
+                            unsigned long long k1x2[TC_CT_MAXN / 2], k2x2[TC_CT_MAXN / 2]; };
 
-struct Quad { float k1[4], i1[4], k2[4], i2[4]; int b[4]; };
+struct Quad { float k1[4], i1[4], k2[4], i2[4]; int b[4]; unsigned long long k1x2[2], k2x2[2]; };
 __device__ __forceinline__ Quad quad_const(const EpiTab& t, int c) {   // c is a compile-time constant after unrolling
     Quad q;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { q.k1[j] = t.k1[c + j]; q.i1[j] = t.i1[c + j]; q.k2[j] = t.k2[c + j]; q.i2[j] = t.i2[c + j]; q.b[j] = t.bias[c + j]; }
+    q.k1x2[0] = t.k1x2[c >> 1]; q.k1x2[1] = t.k1x2[(c >> 1) + 1]; q.k2x2[0] = t.k2x2[c >> 1]; q.k2x2[1] = t.k2x2[(c >> 1) + 1];
     return q;
 }
 __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const int* __restrict__ bias_s, int N, int c) {
@@ -455,6 +463,7 @@ __device__ __forceinline__ Quad quad_smem(const float* __restrict__ tab_s, const
     q.k2[0] = k2.x; q.k2[1] = k2.y; q.k2[2] = k2.z; q.k2[3] = k2.w;
     q.i2[0] = i2.x; q.i2[1] = i2.y; q.i2[2] = i2.z; q.i2[3] = i2.w;
     q.b[0] = b.x; q.b[1] = b.y; q.b[2] = b.z; q.b[3] = b.w;
+    q.k1x2[0] = f2_pack(k1.x, k1.y); q.k1x2[1] = f2_pack(k1.z, k1.w); q.k2x2[0] = f2_pack(k2.x, k2.y); q.k2x2[1] = f2_pack(k2.z, k2.w);
     return q;
 }
 
@@ -481,7 +490,8 @@ __device__ __forceinline__ StoreOff store_off(const ConvArgs& a, int img, int oy
 template <int EPI, bool CT, int FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
-                                             const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u, 0u}) {
+                                             const float* __restrict__ lut_s, const StoreOff so = StoreOff{0u, 0u, 0u, 0u, 0u},
+                                             const EpiPairs cp = EpiPairs{0ull, 0ull, 0ull}) {
     const int M = a.M, N = a.cout;
     const float half = a.half;
     const uint32_t lut_thr = lut_rep_thread_base<5>(smem_u32(lut_s), threadIdx.x & 31u);     // MAGIC2 (loop invariant, hoisted by the compiler)
@@ -494,7 +504,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             for (int j = 0; j < 4; j += 2) {
                 const int v0 = acc[4 * q + j] + cf.b[j], v1 = acc[4 * q + j + 1] + cf.b[j + 1];   // FAST 2: b = bias + magic
                 acc[4 * q + j] = v0; acc[4 * q + j + 1] = v1;
-                silu_magic2_x2<FAST == 3>(v0, v1, f2_pack(cf.k1[j], cf.k1[j + 1]), f2_pack(cf.k2[j], cf.k2[j + 1]), lut_thr, M, r[4 * q + j], r[4 * q + j + 1]);
+                silu_magic2_x2<FAST == 3>(v0, v1, cf.k1x2[j >> 1], cf.k2x2[j >> 1], lut_thr, M, r[4 * q + j], r[4 * q + j + 1], cp);
             }
             continue;
         }
@@ -502,7 +512,7 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
 #pragma unroll
             for (int j = 0; j < 4; j += 2) {
                 const int v0 = acc[4 * q + j] + cf.b[j], v1 = acc[4 * q + j + 1] + cf.b[j + 1];
-                requant_magic_x2<EPI == 2>(v0, v1, f2_pack(cf.k1[j], cf.k1[j + 1]), r[4 * q + j], r[4 * q + j + 1]);
+                requant_magic_x2<EPI == 2>(v0, v1, cf.k1x2[j >> 1], r[4 * q + j], r[4 * q + j + 1], cp);
             }
             continue;
         }

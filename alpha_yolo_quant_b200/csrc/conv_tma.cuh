@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         int buf = CS ? 0 : gk;                                   // tile j = gk, gk + EG, ... of the pipeline -> buffer j % nbuf
         while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         long long d_wt = 0, d_t0 = AYQ_CLK(a);
+        const EpiPairs cp = epi_pairs();                         // packed-epilogue constants, once per thread
         for (int t = blockIdx.x + (grp + (CS ? 0 : 2 * gk)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
             const uint32_t tfull_b = tfull0 + 8 * (TMA_NB * grp + buf), tempty_b = tempty0 + 8 * (TMA_NB * grp + buf);
@@ -332,18 +333,18 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                     tmem_ld_wait16(cur);
                     if (gch + 1 < NBC) tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), nxt);
                     else { tc_fence_before(); mbar_arrive(tempty_b); }   // accumulator fully read: hand it back to the MMA warp
-                    if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
+                    if (valid) epilogue16_t<EPI, true, FAST>(a, et, cur, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so, cp);
                 }
             } else {
                 const int nb = g0 + nbh;
                 for (int gch = g0; gch < nb; gch += 2) {
                     tmem_ld_wait16(accA);
                     tmem_ld16(lane_base + (uint32_t)((gch + 1) * 16), accB);
-                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accA, gch * 16, img, oy, ox, tab_s, bias_s, lut_s, so, cp);
                     tmem_ld_wait16(accB);
                     if (gch + 2 < nb) tmem_ld16(lane_base + (uint32_t)((gch + 2) * 16), accA);
                     else { tc_fence_before(); mbar_arrive(tempty_b); }
-                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s, so);
+                    if (valid) epilogue16_t<EPI, false, FAST>(a, et, accB, (gch + 1) * 16, img, oy, ox, tab_s, bias_s, lut_s, so, cp);
                 }
             }
             buf += CS ? 1 : EG;
@@ -666,6 +667,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
                         L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
                         L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
                     }
+                    for (int c = 0; c + 1 < N; c += 2) { memcpy(&L.et.k1x2[c >> 1], &L.et.k1[c], 8); memcpy(&L.et.k2x2[c >> 1], &L.et.k2[c], 8); }
                 }
                 L.ok = 1;
                 return 1;
@@ -767,6 +769,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
             L.et.k2[c] = fast ? h_tab[2 * N + c] * h_tab[3 * N + c] : h_tab[2 * N + c]; L.et.i2[c] = h_tab[3 * N + c];
             L.et.bias[c] = h_bias[c] + (magic ? AYQ_MAGIC_I : 0);
         }
+        for (int c = 0; c + 1 < N; c += 2) { memcpy(&L.et.k1x2[c >> 1], &L.et.k1[c], 8); memcpy(&L.et.k2x2[c >> 1], &L.et.k2[c], 8); }
     }
     L.ok = 1;
     return 1;

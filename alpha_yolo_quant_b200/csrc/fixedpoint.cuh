@@ -172,32 +172,37 @@ __device__ __forceinline__ void f2_unpack(f32x2_t v, float& a, float& b) { asm("
 __device__ __forceinline__ f32x2_t f2_add_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t f2_mul_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// The three constant pairs of the packed epilogue, materialised ONCE per thread in ordinary register pairs.  (As literals the
+// compiler rebuilt them in uniform registers in front of every use: 37 UMOVs per 32 elements in the ncu source view.)
+struct EpiPairs { f32x2_t neg_c, k32768, half; };
+__device__ __forceinline__ f32x2_t f2_opaque(float v) { f32x2_t r; asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+__device__ __forceinline__ EpiPairs epi_pairs() { EpiPairs p; p.neg_c = f2_opaque(-AYQ_MAGIC_F); p.k32768 = f2_opaque(32768.0f); p.half = f2_opaque(0.5f); return p; }
 // silu_magic2 on elements (v0, v1) of two adjacent channels; k1s / k2p hold the two channels' coefficients
 // I2F: float(acc) by conversion (accumulators beyond 2^22) instead of the magic add; CLAMP: explicit clamp of the result to +-M
 // (a clamp other than 127, or a layer for which the host cannot prove that -128 is unreachable)
 template <bool I2F, bool CLAMP = I2F, int REP_LOG = 5>
-__device__ __forceinline__ void silu_magic2_x2(int v0, int v1, f32x2_t k1s, f32x2_t k2p, uint32_t lut_thr, int M, int& r0, int& r1) {
+__device__ __forceinline__ void silu_magic2_x2(int v0, int v1, f32x2_t k1s, f32x2_t k2p, uint32_t lut_thr, int M, int& r0, int& r1, const EpiPairs& cp) {
     const f32x2_t af = I2F ? f2_pack(__int2float_rn(v0), __int2float_rn(v1))
-                            : f2_add_rn(f2_pack(__int_as_float(v0), __int_as_float(v1)), f2_pack(-AYQ_MAGIC_F, -AYQ_MAGIC_F));
+                            : f2_add_rn(f2_pack(__int_as_float(v0), __int_as_float(v1)), cp.neg_c);
     float t0, t1, y0, y1, w0, w1, l0, l1, z0, z1;
     f2_unpack(f2_mul_rn(k1s, af), t0, t1);
     asm("add.rm.sat.f32 %0, %1, %2;" : "=f"(y0) : "f"(t0), "f"(0.501953125f));
     asm("add.rm.sat.f32 %0, %1, %2;" : "=f"(y1) : "f"(t1), "f"(0.501953125f));
-    f2_unpack(f2_add_rm(f2_pack(y0, y1), f2_pack(32768.0f, 32768.0f)), w0, w1);
+    f2_unpack(f2_add_rm(f2_pack(y0, y1), cp.k32768), w0, w1);
     asm("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"((__float_as_uint(w0) << (2 + REP_LOG)) + lut_thr));
     asm("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"((__float_as_uint(w1) << (2 + REP_LOG)) + lut_thr));
     const f32x2_t pr = f2_mul_rn(f2_pack(l0, l1), af);
-    f2_unpack(f2_add_rm(f2_mul_rn(k2p, pr), f2_pack(0.5f, 0.5f)), z0, z1);
+    f2_unpack(f2_add_rm(f2_mul_rn(k2p, pr), cp.half), z0, z1);
     r0 = floor_sat_s8(z0); r1 = floor_sat_s8(z1);
     if (CLAMP) { r0 = max(-M, min(M, r0)); r1 = max(-M, min(M, r1)); }
 }
 // requantize() of two adjacent channels of a raw accumulator (requant_last_layers / exponent_requant epilogues) with the magic
 // int -> float add and packed multiplies: v = acc + bias + 0x4B400000.  WIDE16: 16-bit result (clamp +-32767), else 8-bit (+-127).
 template <bool WIDE16>
-__device__ __forceinline__ void requant_magic_x2(int v0, int v1, f32x2_t kp, int& r0, int& r1) {
-    const f32x2_t af = f2_add_rn(f2_pack(__int_as_float(v0), __int_as_float(v1)), f2_pack(-AYQ_MAGIC_F, -AYQ_MAGIC_F));
+__device__ __forceinline__ void requant_magic_x2(int v0, int v1, f32x2_t kp, int& r0, int& r1, const EpiPairs& cp) {
+    const f32x2_t af = f2_add_rn(f2_pack(__int_as_float(v0), __int_as_float(v1)), cp.neg_c);
     float z0, z1;
-    f2_unpack(f2_add_rm(f2_mul_rn(kp, af), f2_pack(0.5f, 0.5f)), z0, z1);
+    f2_unpack(f2_add_rm(f2_mul_rn(kp, af), cp.half), z0, z1);
     if (WIDE16) { r0 = max(-32767, floor_sat_s16(z0)); r1 = max(-32767, floor_sat_s16(z1)); }
     else { r0 = max(-127, floor_sat_s8(z0)); r1 = max(-127, floor_sat_s8(z1)); }
 }

@@ -197,7 +197,7 @@ struct P1Args {
 };
 // weights and per-channel epilogue coefficients as a __grid_constant__ parameter: every use below has a compile-time
 // index, so they become constant-bank operands of IDP.4A / FMUL (no weight or coefficient loads in the kernel).
-struct P1Const { unsigned w4[9][16]; float k1[16], i1[16], k2[16], i2[16]; int bias[16]; };
+struct alignas(16) P1Const { unsigned w4[9][16]; float k1[16], i1[16], k2[16], i2[16]; int bias[16]; };
 
 // grid (Wout/32, Hout/8, n), block 256: one 32x8 output tile.  The fp32 input patch (3 x 17 x 65) is read row-wise with
 // coalesced loads, quantised once (quant_matrix) and kept in smem as one packed word (c0,c1,c2,0) per pixel.
