@@ -577,6 +577,9 @@ def main():
     ap.add_argument('--export-main-dir', action='store_true',
                     help='only pack the files the hot path reads, AS THE REFERENCE WROTE THEM (stage_7.py:780 torch.save state_dict, '
                          'utils/save_weights.py:24-30 gzip-pickle bias_scales/, stage_5 max_a.txt), into main_dir_k{K}.tar.xz')
+    ap.add_argument('--time', type=int, default=0, metavar='N',
+                    help='only time the UNMODIFIED stage_8_torch_full_quant forward on N synthetic images (batch 1 per call, all host '
+                         'threads) next to the numpy port on the same machine -> profiles/reference_cpu_r2.json')
     ap.add_argument('--nms-extra', action='store_true',
                     help='only record the crafted q_NMS corner cases and the shipped-argsort detections -> golden_nms_k{K}.npz')
     ap.add_argument('--float-head', type=int, default=0, metavar='N',
@@ -602,6 +605,35 @@ def main():
         gold = capture_weight_quant(work, pkg_root, k, set(args.weight_quant.split(',')))
         np.savez_compressed(os.path.join(args.out, f'golden_wquant_k{k}.npz'), **gold)
         print('[harness] wrote weight-quantiser goldens:', list(gold['layers']))
+        return
+    if args.time:
+        import json
+        g = run_stage(pkg_root, 'stage_8_torch_full_quant.py')
+        model = g['model']
+        xs = [synth.to_input_tensor(synth.synth_image_u8(100 + i)) for i in range(args.time + 1)]
+        with torch.no_grad():
+            model(xs[0])                                            # warm-up
+            t0 = time.time()
+            for x in xs[1:]:
+                model(x)
+            dt_ref = time.time() - t0
+        from oracle import yolo_int as Y
+        o = Y.OracleYolov8(Y.Workload(os.path.join(REPO, 'tests', 'golden', f'workload_k{k}.npz')))
+        xa = [synth.to_input_array([synth.synth_image_u8(100 + i)]) for i in range(args.time + 1)]
+        o.forward(xa[0])
+        t0 = time.time()
+        for x in xa[1:]:
+            o.forward(x)
+        dt_port = time.time() - t0
+        out = {'cores': os.cpu_count(), 'images': args.time,
+               'reference_unmodified_images_per_s': args.time / dt_ref, 'port_single_process_images_per_s': args.time / dt_port,
+               'what': 'unmodified stage_8_torch_full_quant.Yolov8.forward (torch CPU ops, torch.set_num_threads(all cores), batch 1 per call) vs '
+                       'oracle/yolo_int.py (numpy, one process) on the same synthetic images in the build container; bench.py times the port '
+                       'with one worker process per core on the GPU box, where /root/reference does not exist',
+               'versions': f'torch {torch.__version__} numpy {np.__version__}'}
+        os.makedirs(os.path.join(REPO, 'profiles'), exist_ok=True)
+        json.dump(out, open(os.path.join(REPO, 'profiles', 'reference_cpu_r2.json'), 'w'), indent=1)
+        print('[harness]', out)
         return
     if args.export_main_dir:
         import tarfile
