@@ -495,6 +495,7 @@ static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a) {
     if (f[CF_ACC_BUF] >= 0) a.acc_tap = (int*)(e->ws + e->buf_off[f[CF_ACC_BUF]]);   // raw accumulators feed the float head
     a.half = 0.5f;
     a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * 16 : nullptr;
+    a.dbg_mode = getenv("AYQ_EPI_SKIP") ? atoi(getenv("AYQ_EPI_SKIP")) : 0;
 }
 // tensor maps + stage plan of conv op `opi` for passes of n images (cached); returns L.ok
 static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {

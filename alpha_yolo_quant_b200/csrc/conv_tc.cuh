@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         if (it > (1u << 23)) __trap();
     }
 }
+// (Tried and dropped: parking the long waits on a dependent uncached global load instead of nanosleep -- the loads return in ~150
+// cycles from the L2, the loop issued as many instructions as before.  A failed try_wait's hardware suspend ends at EVERY mbarrier
+// completion of the CTA, ~21 wake-ups per tile: that is what the polling costs, whatever sits between the probes.)
 // named barrier of one epilogue group (four warps): id 1.. (0 is __syncthreads)
 __device__ __forceinline__ void group_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -487,6 +490,25 @@ __device__ __forceinline__ StoreOff store_off(const ConvArgs& a, int img, int oy
     return so;
 }
 
+// The same, split into what depends on the THREAD (its pixel inside the tile: computed once per kernel) and what depends on the TILE
+// (three multiply-adds per tile): valid when the tile origin is even in x and y (every tile shape the host picks is: tile widths /
+// heights are powers of two >= 2, or the 8 x 16 halo tile), which the caller checks.
+struct StoreOffThread { uint32_t pix16, ps_pix16; };
+__device__ __forceinline__ StoreOffThread store_off_thread(const ConvArgs& a, int dn, int dy, int dx) {
+    StoreOffThread t;
+    t.pix16 = (((uint32_t)dn * (uint32_t)a.Hout + (uint32_t)dy) * (uint32_t)a.Wout + (uint32_t)dx) * 16u;
+    const uint32_t H2 = (uint32_t)a.Hout >> 1, W2 = (uint32_t)a.Wout >> 1;
+    const uint32_t ph = (uint32_t)(((dy & 1) << 1) | (dx & 1)) * ((uint32_t)a.cout >> 4);
+    t.ps_pix16 = (((ph * (uint32_t)a.n + (uint32_t)dn) * H2 + (uint32_t)(dy >> 1)) * W2 + (uint32_t)(dx >> 1)) * 16u;
+    return t;
+}
+__device__ __forceinline__ StoreOff store_off_tile(const ConvArgs& a, const StoreOff& inv, const StoreOffThread& th, int img0, int y0, int x0) {
+    StoreOff so = inv;                                            // plane16 / ps_plane16 / mode: loop invariant
+    so.pix16 = th.pix16 + (((uint32_t)img0 * (uint32_t)a.Hout + (uint32_t)y0) * (uint32_t)a.Wout + (uint32_t)x0) * 16u;
+    so.ps_pix16 = th.ps_pix16 + (((uint32_t)img0 * ((uint32_t)a.Hout >> 1) + ((uint32_t)y0 >> 1)) * ((uint32_t)a.Wout >> 1) + ((uint32_t)x0 >> 1)) * 16u;
+    return so;
+}
+
 template <int EPI, bool CT, int FAST>
 __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et, int* acc, int c0, int img, int oy, int ox,
                                              const float* __restrict__ tab_s, const int* __restrict__ bias_s,
@@ -499,6 +521,13 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const Quad cf = CT ? quad_const(et, c0 + 4 * q) : quad_smem(tab_s, bias_s, N, c0 + 4 * q);
+#ifdef AYQ_ROLE_PROF_BUILD
+        if (a.dbg_mode == 1) {                                     // experiment: what does the kernel cost WITHOUT the epilogue arithmetic?
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[4 * q + j] = (acc[4 * q + j] + cf.b[j]) & 0x7f;
+            continue;
+        }
+#endif
         if (EPI == 0 && FAST >= 2) {                               // MAGIC2 / WIDE: two channels per packed-FP32 instruction
 #pragma unroll
             for (int j = 0; j < 4; j += 2) {

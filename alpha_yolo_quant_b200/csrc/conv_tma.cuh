@@ -306,13 +306,16 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         long long d_wt = 0, d_t0 = AYQ_CLK(a);
         const EpiPairs cp = epi_pairs();                         // packed-epilogue constants, once per thread
+        const StoreOff so_inv = FAST ? store_off(a, 0, 0, 0) : StoreOff{0u, 0u, 0u, 0u, 0u};   // its loop-invariant fields
+        const StoreOffThread so_th = store_off_thread(a, dn, dy, dx);
         for (int t = blockIdx.x + (grp + (CS ? 0 : 2 * gk)) * gridDim.x; t < tp.ntiles; t += tstep * gridDim.x) {
             const uint32_t lane_base = lane_quad + (uint32_t)((grp * nbuf + buf) * N);
             const uint32_t tfull_b = tfull0 + 8 * (TMA_NB * grp + buf), tempty_b = tempty0 + 8 * (TMA_NB * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
             const bool valid = img < a.n && oy < a.Hout;          // overhanging tiles: images past the batch, rows past the map (halo mode)
-            const StoreOff so = FAST ? store_off(a, img, oy, ox) : StoreOff{0u, 0u, 0u, 0u, 0u};   // per-tile part of the store addresses
+            const StoreOff so = !FAST ? StoreOff{0u, 0u, 0u, 0u, 0u}                                // per-tile part of the store addresses
+                                : (((tc0.x0 | tc0.y0) & 1) == 0 ? store_off_tile(a, so_inv, so_th, tc0.img0, tc0.y0, tc0.x0) : store_off(a, img, oy, ox));
             const long long w0 = AYQ_CLK(a);
             // ONE warp of the group polls the accumulator barrier; the other three park in a hardware barrier that costs no issue
             // slots (every polling warp re-executes its probe loop whenever any barrier of the CTA changes: measured 8 % of all

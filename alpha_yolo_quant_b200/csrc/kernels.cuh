@@ -41,6 +41,7 @@ struct ConvArgs {
     float half;                 // 0.5f, kept in a register by the fast epilogues (see silu_q127)
     long long* dbg;             // AYQ_ROLE_PROF=1: per-CTA cycle counters of the warp roles [grid][16], else nullptr
     int gen_outs;               // MAGIC epilogue only: 1 = general output list (requantised copies through 256-byte tables, upsample)
+    int dbg_mode;               // profiling build only (AYQ_EPI_SKIP=1): 1 = skip the fixed-point arithmetic, store the low accumulator bytes
 };
 
 // byte offset of the 16-byte row (channels [c0, c0+16) of output pixel (img, oy, ox)) in a phase-split buffer
