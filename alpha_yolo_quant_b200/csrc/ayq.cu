@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <algorithm>
 
 #include "../../include/ayq.h"
 #include "plan_format.h"
@@ -44,6 +45,8 @@ struct ayq_engine {
     std::vector<OpDesc> ops;
     std::vector<unsigned char> host_data;
     unsigned char* d_data = nullptr;       // data section on the device
+    float* d_lutrep = nullptr;             // replicated sigmoid tables (one [257][32] + one [257][8] block per distinct table of the plan)
+    std::vector<const float*> op_lutrep;   // per op: its [257][32] block (convs with the SiLU epilogue) / [257][8] block (Conv_P1), else nullptr
     int max_batch = 256;
     int cap = 0;                           // images the workspace is sized for
     unsigned char* ws = nullptr;
@@ -297,7 +300,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(-19, "ayq_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     ayq_engine* e = new ayq_engine();
-    struct Guard { ayq_engine* e; ~Guard() { if (e) { if (e->d_data) cudaFree(e->d_data); if (e->ev_busy) cudaEventDestroy(e->ev_busy); if (e->d_role) cudaFree(e->d_role); delete e; } } } guard{e};
+    struct Guard { ayq_engine* e; ~Guard() { if (e) { if (e->d_data) cudaFree(e->d_data); if (e->d_lutrep) cudaFree(e->d_lutrep); if (e->ev_busy) cudaEventDestroy(e->ev_busy); if (e->d_role) cudaFree(e->d_role); delete e; } } } guard{e};
     e->device = device;
     e->hdr = h;
     e->bufs.resize(h.n_bufs);
@@ -309,6 +312,41 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
         cudaMemcpy(e->d_data, e->host_data.data(), h.data_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(-12, "ayq_create: cannot upload %llu bytes of plan data", (unsigned long long)h.data_bytes);
     CK(cudaEventCreateWithFlags(&e->ev_busy, cudaEventDisableTiming));
+    {   // replicated sigmoid tables: entry i of a block = table[clamp(i - 128, -M, M) + M], 32 (convs) or 8 (Conv_P1) copies each
+        std::map<std::pair<int, int>, size_t> seen;               // (table offset, M) -> float offset of its two blocks
+        std::vector<float> rep;
+        const size_t blk = (size_t)AYQ_LUTREP_N * 32 + (size_t)AYQ_LUTREP_N * 8;
+        e->op_lutrep.assign(h.n_ops, nullptr);
+        std::vector<size_t> op_off(h.n_ops, (size_t)-1);
+        for (uint32_t i = 0; i < h.n_ops; ++i) {
+            const int32_t* f = e->ops[i].f;
+            int off, M;
+            if (f[0] == OP_CONV && f[CF_EPI] == 0) { off = f[CF_LUT_OFF]; M = f[CF_CLAMP]; }
+            else if (f[0] == OP_CONV_P1) { off = f[P1_LUT_OFF]; M = f[P1_CLAMP]; }
+            else continue;
+            if (M < 1 || M > 127) continue;
+            auto key = std::make_pair(off, M);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                const float* t = (const float*)(e->host_data.data() + off);
+                const size_t base = rep.size();
+                rep.resize(base + blk);
+                for (int j = 0; j < AYQ_LUTREP_N; ++j) {
+                    const int r = std::max(-M, std::min(M, j - 128));
+                    for (int c = 0; c < 32; ++c) rep[base + (size_t)j * 32 + c] = t[r + M];
+                    for (int c = 0; c < 8; ++c) rep[base + (size_t)AYQ_LUTREP_N * 32 + (size_t)j * 8 + c] = t[r + M];
+                }
+                it = seen.emplace(key, base).first;
+            }
+            op_off[i] = it->second + (f[0] == OP_CONV_P1 ? (size_t)AYQ_LUTREP_N * 32 : 0);
+        }
+        if (!rep.empty()) {
+            if (cudaMalloc(&e->d_lutrep, rep.size() * sizeof(float)) != cudaSuccess ||
+                cudaMemcpy(e->d_lutrep, rep.data(), rep.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(-12, "ayq_create: cannot upload the replicated sigmoid tables");
+            for (uint32_t i = 0; i < h.n_ops; ++i) if (op_off[i] != (size_t)-1) e->op_lutrep[i] = e->d_lutrep + op_off[i];
+        }
+    }
 #ifdef AYQ_TEST_BUILD
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(conv_dp4a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -332,8 +370,8 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
     }
     if (e->role_prof) {
         e->use_graph = false;
-        CK(cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * 16));
-        CK(cudaMemset(e->d_role, 0, sizeof(long long) * h.n_ops * 148 * 16));
+        CK(cudaMalloc(&e->d_role, sizeof(long long) * h.n_ops * 148 * AYQ_DBG_SLOTS));
+        CK(cudaMemset(e->d_role, 0, sizeof(long long) * h.n_ops * 148 * AYQ_DBG_SLOTS));
     }
     g_pdl = getenv("AYQ_NO_PDL") == nullptr ? 1 : 0;
     tc_init(e->tc);
@@ -363,7 +401,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
     cudaSetDevice(e->device);
     if (e->role_prof && e->d_role) {
         cudaDeviceSynchronize();
-        std::vector<long long> h((size_t)e->ops.size() * 148 * 16);
+        std::vector<long long> h((size_t)e->ops.size() * 148 * AYQ_DBG_SLOTS);
         cudaMemcpy(h.data(), e->d_role, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         fprintf(stderr, "role profile of the last pass (kilo-cycles, mean over CTAs): op name | prod0 total/wait_empty | prod1 | mma0 total/wait_tempty/wait_full | mma1 | epi0 total/wait_tfull | epi1\n");
         for (size_t i = 0; i < e->ops.size(); ++i) {
@@ -371,7 +409,7 @@ extern "C" int ayq_destroy(ayq_handle e) {
             double m[16] = {0};
             int cnt = 0;
             for (int b = 0; b < 148; ++b) {
-                const long long* r = &h[(i * 148 + b) * 16];
+                const long long* r = &h[(i * 148 + b) * AYQ_DBG_SLOTS];
                 if (r[6] == 0) continue;
                 ++cnt;
                 for (int k = 0; k < 16; ++k) m[k] += (double)r[k];
@@ -383,10 +421,54 @@ extern "C" int ayq_destroy(ayq_handle e) {
                     m[6] / cnt / 1e3, m[7] / cnt / 1e3, m[8] / cnt / 1e3, m[9] / cnt / 1e3, m[10] / cnt / 1e3, m[11] / cnt / 1e3,
                     m[12] / cnt / 1e3, m[13] / cnt / 1e3, m[14] / cnt / 1e3, m[15] / cnt / 1e3);
         }
+        // kernel-to-kernel timeline from the globaltimer stamps (us): how the fixed cost of a launch splits up
+        fprintf(stderr, "timeline of the last pass (us): op | span = last exit - first entry | prologue (mean) | dependency wait (mean) | body = wait done -> exit (mean) | "
+                        "exit spread: last - mean, last - first | gap: this op's first 'wait done' - previous conv's last exit\n");
+        long long prev_last_exit = 0, prev_first_exit = 0;
+        double sum_span = 0, sum_body = 0, sum_tail = 0, sum_gap = 0;
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            if (e->ops[i].f[0] != OP_CONV) continue;
+            long long first_in = 0, last_out = 0, first_out = 0, first_go = 0;
+            double pro = 0, wt = 0, body = 0, mean_out = 0;
+            int cnt = 0;
+            for (int b = 0; b < 148; ++b) {
+                const long long* r = &h[(i * 148 + b) * AYQ_DBG_SLOTS];
+                if (r[16] == 0 || r[19] == 0) continue;
+                if (!cnt || r[16] < first_in) first_in = r[16];
+                if (!cnt || r[19] > last_out) last_out = r[19];
+                if (!cnt || r[19] < first_out) first_out = r[19];
+                if (!cnt || r[18] < first_go) first_go = r[18];
+                pro += (double)(r[17] - r[16]); wt += (double)(r[18] - r[17]); body += (double)(r[19] - r[18]);
+                ++cnt;
+            }
+            if (!cnt) continue;
+            for (int b = 0; b < 148; ++b) { const long long* r = &h[(i * 148 + b) * AYQ_DBG_SLOTS]; if (r[16] && r[19]) mean_out += (double)(r[19] - first_in); }
+            mean_out /= cnt;
+            const char* nm = (const char*)(e->host_data.data() + e->ops[i].f[CF_NAME_OFF]);
+            const double gap = prev_last_exit ? (double)(first_go - prev_last_exit) / 1e3 : 0.0;
+            fprintf(stderr, "%3zu %-20s | %7.2f | %6.2f | %6.2f | %7.2f | %6.2f %6.2f | %6.2f | entry-prev first exit %6.2f, entry-prev last exit %6.2f\n", i, nm, (double)(last_out - first_in) / 1e3, pro / cnt / 1e3, wt / cnt / 1e3,
+                    body / cnt / 1e3, ((double)(last_out - first_in) - mean_out) / 1e3, (double)(last_out - first_out) / 1e3, gap,
+                    prev_last_exit ? (double)(first_in - prev_first_exit) / 1e3 : 0.0, prev_last_exit ? (double)(first_in - prev_last_exit) / 1e3 : 0.0);
+            sum_span += (double)(last_out - first_in) / 1e3; sum_body += body / cnt / 1e3; sum_tail += ((double)(last_out - first_in) - mean_out) / 1e3;
+            if (prev_last_exit && gap < 100.0) sum_gap += gap;
+            prev_last_exit = last_out; prev_first_exit = first_out;
+        }
+        if (const char* path = getenv("AYQ_TIMELINE_RAW")) {          // every CTA's four stamps (ns), one line per (op, CTA)
+            if (FILE* fp = fopen(path, "w")) {
+                for (size_t i = 0; i < e->ops.size(); ++i)
+                    for (int b = 0; b < 148; ++b) {
+                        const long long* r = &h[(i * 148 + b) * AYQ_DBG_SLOTS];
+                        if (r[16]) fprintf(fp, "%zu %d %lld %lld %lld %lld %lld\n", i, b, r[16], r[17], r[18], r[19], r[20]);
+                    }
+                fclose(fp);
+            }
+        }
+        fprintf(stderr, "timeline sums (us): span %.1f, mean body %.1f, exit spread (last - mean) %.1f, gaps %.1f\n", sum_span, sum_body, sum_tail, sum_gap);
         cudaFree(e->d_role);
     }
     free_workspace(e);
     if (e->d_data) cudaFree(e->d_data);
+    if (e->d_lutrep) cudaFree(e->d_lutrep);
     for (int i = 0; i < 2; ++i) {
         if (e->d_img[i]) cudaFree(e->d_img[i]);
         if (e->d_img_u8[i]) cudaFree(e->d_img_u8[i]);
@@ -479,6 +561,7 @@ static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a) {
     a.bias = (const int*)(e->d_data + f[CF_BIAS_OFF]);
     a.tab = (const float*)(e->d_data + f[CF_TAB_OFF]);
     a.lut = (const float*)(e->d_data + f[CF_LUT_OFF]);
+    a.lut_rep = e->op_lutrep[opi];
     a.n = n; a.Hin = f[CF_HIN]; a.Win = f[CF_WIN]; a.Hout = f[CF_HOUT]; a.Wout = f[CF_WOUT];
     a.stride = f[CF_STRIDE]; a.cout = f[CF_COUT]; a.epi = f[CF_EPI]; a.M = f[CF_CLAMP];
     a.nout = f[CF_NOUT];
@@ -494,7 +577,7 @@ static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a) {
     a.acc_tap = f[CF_ACC_TAP] >= 0 ? e->acc_taps[f[CF_ACC_TAP]] : nullptr;
     if (f[CF_ACC_BUF] >= 0) a.acc_tap = (int*)(e->ws + e->buf_off[f[CF_ACC_BUF]]);   // raw accumulators feed the float head
     a.half = 0.5f;
-    a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * 16 : nullptr;
+    a.dbg = e->role_prof ? e->d_role + (size_t)opi * 148 * AYQ_DBG_SLOTS : nullptr;
     a.dbg_mode = getenv("AYQ_EPI_SKIP") ? atoi(getenv("AYQ_EPI_SKIP")) : 0;
 }
 // tensor maps + stage plan of conv op `opi` for passes of n images (cached); returns L.ok
@@ -586,6 +669,7 @@ static int launch_op(ayq_engine* e, size_t i, const PassArgs& pa, cudaStream_t s
         P1Args a;
         a.img = img; a.img_u8 = pa.img_u8; a.amax = amax;
         a.lut = (const float*)(e->d_data + f[P1_LUT_OFF]);
+        a.lut_rep8 = e->op_lutrep[i];
         a.n = n; a.H = H; a.W = W; a.Hout = f[P1_HOUT]; a.Wout = f[P1_WOUT]; a.M = f[P1_CLAMP];
         a.out = (int8_t*)(e->ws + e->buf_off[f[P1_OUT_BUF]]);
         a.acc_tap = f[P1_ACC_TAP] >= 0 ? e->acc_taps[f[P1_ACC_TAP]] : nullptr;

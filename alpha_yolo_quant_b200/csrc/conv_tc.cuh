@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(P1TC_THREADS) conv_p1_tc_kernel(const __grid_c
         if (ia < a.fuse_d || ia - a.fuse_d >= a.n) return;        // nothing to convolve for this ticket (nothing allocated yet: plain exit)
         img = ia - a.fuse_d; y0 = band * P1_TH;
     }
-    fill_lut_rep<3>(lut_rep, a.lut, a.M, tid, P1TC_THREADS);
+    // sigmoid table, eight copies per entry: built once per engine in global memory, copied with independent 16-byte loads (filling it
+    // from the 255-entry table cost seven dependent L2 round trips per CTA)
+    for (int i = tid; i < AYQ_LUTREP_N * 8 / 4; i += P1TC_THREADS) ((uint4*)lut_rep)[i] = __ldg((const uint4*)a.lut_rep8 + i);
     if (tid < 256) ((uint2*)&sB[0][0][0])[tid] = ((const uint2*)&wb)[tid];
     if (tid == 0) {
         mbar_init(smem_u32(&bar), 1);
@@ -556,6 +558,15 @@ __device__ __forceinline__ void epilogue16_t(const ConvArgs& a, const EpiTab& et
             else r[4 * q + j] = FAST ? requant16_f(__int2float_rn(v), cf.k1[j], half) : requant16(__int2float_rn(v), cf.k1[j], cf.i1[j]);
         }
     }
+#ifdef AYQ_ROLE_PROF_BUILD
+    if (a.dbg_mode & 16) {                                         // experiment: all the arithmetic, no stores
+        int sx = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sx ^= r[j];
+        if (sx == 0x12345678) *(int*)a.out[0].base = sx;
+        return;
+    }
+#endif
     if (FAST) {                       // every output buffer is < 4 GB (checked by the host): 32-bit offsets, per-tile part in `so`
         const uint32_t npix = so.plane16 >> 4;
         const uint32_t off = (uint32_t)(c0 >> 4) * so.plane16 + so.pix16;

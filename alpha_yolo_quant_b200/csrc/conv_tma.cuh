@@ -24,12 +24,17 @@ namespace tc {
 
 // Role-level cycle counters (AYQ_ROLE_PROF=1) exist only in the profiling build of the library (libayq_prof.so, built with
 // -DAYQ_ROLE_PROF_BUILD): a predicated-off clock read still costs an issue slot, and these sit in every per-tile loop.
+#define AYQ_DBG_SLOTS 24          // per CTA: 16 role counters + 4 globaltimer stamps (entry, prologue done, dependency wait done, exit)
 #ifdef AYQ_ROLE_PROF_BUILD
 #define AYQ_DBG(a) ((a).dbg != nullptr)
+#define AYQ_STAMP(a, k) do { if ((a).dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (a).dbg[blockIdx.x * AYQ_DBG_SLOTS + 16 + (k)] = (long long)t_; } } while (0)
 #define AYQ_CLK(a) ((a).dbg ? clock64() : 0)
+#define AYQ_XMODE(a, bit) (((a).dbg_mode & (bit)) != 0)     // experiments (AYQ_EPI_SKIP bit mask): 2 no epilogue work, 4 no loads, 8 no MMAs
 #else
 #define AYQ_DBG(a) false
+#define AYQ_STAMP(a, k) do { } while (0)
 #define AYQ_CLK(a) 0ll
+#define AYQ_XMODE(a, bit) false
 #endif
 
 constexpr int TMA_MAX_MAPS = 8;
@@ -96,8 +101,12 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                                                                   const __grid_constant__ EpiTab et, const __grid_constant__ TmaPlan pl,
                                                                   const __grid_constant__ TmaMaps maps) {
     constexpr int TMA_THREADS = 256 + 256 * EG;
+#ifdef AYQ_ROLE_PROF_BUILD
+    unsigned long long t_entry_;                                   // first instruction of the CTA, before any parameter is touched
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry_));
+#endif
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 2 * 2 * TMA_NB + 1];   // full[NS], empty[NS], tfull[2][NB], tempty[2][NB], wfull
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_NS + 2 * 2 * TMA_NB + 2];   // full[NS], empty[NS], tfull[2][NB], tempty[2][NB], wfull, lfull
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31;
     // Role of a warp.  The SMSP arbiter favours the highest warp ids, so with role_hi the eight control warps (MMA issuers, TMA
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     int* bias_s = (int*)(tab_s + 4 * N);
     float* lut_s = (float*)(bias_s + N);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_NS]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2 * TMA_NB]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4 * TMA_NB]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_NS]), tempty0 = smem_u32(&bars[2 * TC_MAX_NS + 2 * TMA_NB]), wfull = smem_u32(&bars[2 * TC_MAX_NS + 4 * TMA_NB]), lfull = wfull + 8;
     // TMEM accumulator ring of a pipeline: tile j of the pipeline (j = 0, 1, ...) lands in buffer j % nbuf and is drained by
     // epilogue group j % EG.  nbuf = 2 * EG where the 512 columns allow it: a group then never waits for the refill of the buffer
     // it has just handed back (barrier hand-off + MMA issue + MMA execution, several hundred cycles) -- its next tile is already
@@ -124,6 +133,10 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     const int nbuf = tp.nbuf;
 
     pdl_trigger();
+    AYQ_STAMP(a, 0);
+#ifdef AYQ_ROLE_PROF_BUILD
+    if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 20] = (long long)t_entry_;
+#endif
     // ---- prologue: touches only engine constants (tables, weights), so it may overlap the previous kernel's tail ----
     if (NBC == 0) {
         if (FAST) {                                                 // folded coefficients: rows 0 / 2 hold k * 2^-s (exact)
@@ -139,7 +152,16 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         for (int i = tid; i < N; i += TMA_THREADS) bias_s[i] = a.bias[i] + (FAST == 2 ? AYQ_MAGIC_I : 0);
     }
     if (EPI == 0 && FAST >= 2) {
-        fill_lut_rep(lut_s, a.lut, a.M, tid, TMA_THREADS);         // per-lane replicated sigmoid table (fixedpoint.cuh: silu_magic2)
+        // per-lane replicated sigmoid table (fixedpoint.cuh: silu_magic2): the engine built it once in global memory, two bulk copies
+        // bring its 32.1 KB in while the rest of the prologue runs (filling it from the 255-entry table with dependent loads took
+        // ~2 us per CTA, all of it between the previous kernel's last store and this kernel's first load)
+        if (warp == 3 && lane == 0) {
+            mbar_init(lfull, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_arrive_expect_tx(lfull, (uint32_t)AYQ_LUTREP_BYTES);
+            bulk_g2s(smem_u32(lut_s), a.lut_rep, AYQ_LUTREP_BYTES / 2, lfull);
+            bulk_g2s(smem_u32(lut_s) + AYQ_LUTREP_BYTES / 2, (const unsigned char*)a.lut_rep + AYQ_LUTREP_BYTES / 2, AYQ_LUTREP_BYTES / 2, lfull);
+        }
         if (a.gen_outs) {                                          // 256-byte table per requantised output: index = SiLU result + 128
             unsigned char* rq = (unsigned char*)lut_s + AYQ_LUTREP_BYTES;
             for (int i = tid; i < 256 * a.nout; i += TMA_THREADS) {
@@ -176,7 +198,9 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    AYQ_STAMP(a, 1);
     pdl_wait();                                                     // activations of the previous layer are complete from here on
+    AYQ_STAMP(a, 2);
 
     // Two pipelines share the CTA: pipeline m (m = 0, 1) owns the tiles i with i % 2 == m, its accumulator ring in TMEM and its EG
     // epilogue groups.  Each pipeline is fed by TWO independent chains (q = 0, 1: the pipeline's even / odd tiles), each chain =
@@ -205,7 +229,8 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 const long long w0 = AYQ_CLK(a);
                 mbar_wait_relaxed<768>(empty0 + 8 * gs, ephase);
                 if (AYQ_DBG(a)) d_wait += clock64() - w0;
-                if (elect_one()) {
+                if (AYQ_XMODE(a, 4)) { if (elect_one()) mbar_arrive(full0 + 8 * gs); }
+                else if (elect_one()) {
                     const uint32_t bar = full0 + 8 * gs;
                     const uint32_t nch_b = (uint32_t)((sg.nchunks + 1) & ~1);
                     mbar_arrive_expect_tx(bar, (pl.halo ? (uint32_t)pl.halo_tx_bytes : (uint32_t)sg.nchunks * 2048u) + (tp.resident_b ? 0u : nch_b * N * 16u));
@@ -222,7 +247,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 if (++slot == NSQ) { slot = 0; ephase ^= 1; }
             }
         }
-        if (AYQ_DBG(a) && lane == 0 && q == 0) { a.dbg[blockIdx.x * 16 + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + m * 2 + 1] = d_wait; }
+        if (AYQ_DBG(a) && lane == 0 && q == 0) { a.dbg[blockIdx.x * AYQ_DBG_SLOTS + m * 2] = clock64() - d_t0; a.dbg[blockIdx.x * AYQ_DBG_SLOTS + m * 2 + 1] = d_wait; }
     } else if (warp < 2 || warp == 6 || warp == 7) {
         // ===== MMA issuer of chain (m, par): warp-uniform control flow, one elected lane issues; the descriptor low words (address |
         // LBO) are stepped with 32-bit adds.  Warps m and 6 + m issue the even / odd tiles of pipeline m from their private rings; the
@@ -264,7 +289,8 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
                 tc_fence_after();
                 if (elect_one()) {
                     uint32_t acc = accum;
-                    if (pl.halo) {
+                    if (AYQ_XMODE(a, 8)) { }
+                    else if (pl.halo) {
                         const uint32_t abase = ((smem_u32(sA) & 0x3ffffu) >> 4) + (uint32_t)gs * a_step;
                         const int n_hmma = pl.n_hmma;
                         for (int j = 0; j < n_hmma; ++j) {
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             buf += nq;
             if (buf >= nbuf) { buf -= nbuf; ephase ^= 1u; }
         }
-        if (AYQ_DBG(a) && lane == 0 && par == 0) { a.dbg[blockIdx.x * 16 + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * 16 + 8 + 3 * m] = d_wf; }
+        if (AYQ_DBG(a) && lane == 0 && par == 0) { a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 6 + 3 * m] = clock64() - d_t0; a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 7 + 3 * m] = d_we; a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 8 + 3 * m] = d_wf; }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> fixed-point SiLU / requant -> 16-byte plane rows =====
         const int gq = (warp - 8) >> 2;
@@ -305,6 +331,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
         int buf = CS ? 0 : gk;                                   // tile j = gk, gk + EG, ... of the pipeline -> buffer j % nbuf
         while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         long long d_wt = 0, d_t0 = AYQ_CLK(a);
+        if (EPI == 0 && FAST >= 2) mbar_wait(lfull, 0);          // the sigmoid table has landed (prologue bulk copy)
         const EpiPairs cp = epi_pairs();                         // packed-epilogue constants, once per thread
         const StoreOff so_inv = FAST ? store_off(a, 0, 0, 0) : StoreOff{0u, 0u, 0u, 0u, 0u};   // its loop-invariant fields
         const StoreOffThread so_th = store_off_thread(a, dn, dy, dx);
@@ -313,7 +340,7 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             const uint32_t tfull_b = tfull0 + 8 * (TMA_NB * grp + buf), tempty_b = tempty0 + 8 * (TMA_NB * grp + buf);
             const TileCoord tc0 = tile_coord(t, tp);
             const int img = tc0.img0 + dn, oy = tc0.y0 + dy, ox = tc0.x0 + dx;
-            const bool valid = img < a.n && oy < a.Hout;          // overhanging tiles: images past the batch, rows past the map (halo mode)
+            const bool valid = img < a.n && oy < a.Hout && !AYQ_XMODE(a, 2);          // overhanging tiles: images past the batch, rows past the map (halo mode)
             const StoreOff so = !FAST ? StoreOff{0u, 0u, 0u, 0u, 0u}                                // per-tile part of the store addresses
                                 : (((tc0.x0 | tc0.y0) & 1) == 0 ? store_off_tile(a, so_inv, so_th, tc0.img0, tc0.y0, tc0.x0) : store_off(a, img, oy, ox));
             const long long w0 = AYQ_CLK(a);
@@ -353,9 +380,18 @@ __global__ void __launch_bounds__(256 + 256 * EG, 1) conv_tma_kernel(const __gri
             buf += CS ? 1 : EG;
             while (buf >= nbuf) { buf -= nbuf; tphase ^= 1u; }
         }
-        if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gk == 0) { a.dbg[blockIdx.x * 16 + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * 16 + 13 + 2 * grp] = d_wt; }
+        if (AYQ_DBG(a) && (warp & 3) == 0 && lane == 0 && gk == 0) { a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 12 + 2 * grp] = clock64() - d_t0; a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 13 + 2 * grp] = d_wt; }
     }
     tc_fence_before();
+#ifdef AYQ_ROLE_PROF_BUILD
+    // exit stamp = arrival of the CTA's LAST warp at the final barrier.  (A stamp read by one thread after the barrier is not that:
+    // BAR.SYNC.DEFER_BLOCKING lets a warp run ahead to the next instruction that needs the barrier, and a timer read does not.)
+    if (a.dbg && lane == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) :: "memory");
+        atomicMax((unsigned long long*)&a.dbg[blockIdx.x * AYQ_DBG_SLOTS + 19], t_);
+    }
+#endif
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -471,11 +507,15 @@ static inline bool magic_epilogue_ok(const ConvArgs& a, const float* h_tab, cons
 
 static inline void tma_init(TmaState& s) {
     const int ns[] = {16, 32, 64, 80, 128};
+    const bool carve = getenv("AYQ_CARVEOUT") != nullptr && atoi(getenv("AYQ_CARVEOUT")) != 0;
     for (int epi = 0; epi < 3; ++epi)
         for (int N : ns)
             for (int fast = 0; fast < 4; ++fast) {
                 TmaKernel k = tma_pick(N, epi, fast);
                 if (k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+                // one L1 / shared-memory split for every conv launch: consecutive kernels with different dynamic sizes otherwise
+                // get different carve-outs, and an SM re-partitions only when idle (measured: see DESIGN.md, launch-to-launch gap)
+                if (k && carve) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             }
     int dev = 0;
     cudaGetDevice(&dev);
@@ -782,6 +822,14 @@ static inline int tma_launch(const TmaLaunch& L, const ConvArgs& a, cudaStream_t
     TmaKernel kern = tma_pick(a.cout, a.epi, L.fast);
     ConvArgs a2 = a;
     a2.gen_outs = L.gen_outs;
+#ifdef AYQ_ROLE_PROF_BUILD
+    static const int skip_tiles = getenv("AYQ_SKIP_TILES") ? atoi(getenv("AYQ_SKIP_TILES")) : 0;   // experiment: prologue + exit only (results are garbage)
+    if (skip_tiles) {
+        tc::TcParams tp0 = L.tp;
+        { const long long cap = (long long)(skip_tiles - 1) * (long long)L.grid; if (cap < tp0.ntiles) tp0.ntiles = (int)cap; }   // k - 1 tiles per CTA
+        return launch_k(kern, dim3(L.grid), dim3(256 + 256 * tma_eg(a.cout, a.epi)), L.smem, st, a2, tp0, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
+    }
+#endif
     return launch_k(kern, dim3(L.grid), dim3(256 + 256 * tma_eg(a.cout, a.epi)), L.smem, st, a2, L.tp, L.et, L.pl, L.maps) == cudaSuccess ? 0 : -1;
 }
 

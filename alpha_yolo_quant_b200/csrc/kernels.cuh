@@ -35,6 +35,7 @@ struct ConvArgs {
     size_t in_plane_bytes;      // n * Hin * Win * 16
     const int8_t* w;            // [nkc_pad][cout][16]
     const int* bias; const float* tab; const float* lut;
+    const float* lut_rep;       // the sigmoid table replicated per lane ([257][32], fixedpoint.cuh), built once per engine: one bulk copy in the prologue
     int n, Hin, Win, Hout, Wout, stride, cout, epi, M;
     int nout; OutSpec out[3];
     int* acc_tap;               // NCHW int32 (n, cout, Hout, Wout) or nullptr
@@ -189,6 +190,7 @@ struct P1Args {
     unsigned* sync;             // fused kernel: {ticket, band counter per image}, zeroed by the host
     int fuse_d;                 // fused kernel: images between the abs-max step and the convolution step of a ticket (0 or 1)
     const float* lut;           // sigmoid table [2M+1]
+    const float* lut_rep8;      // the same, eight copies per entry ([257][8]), built once per engine
     int n, H, W, Hout, Wout, M;
     int8_t* out;                // plane buffer (1 plane) (n,Hout,Wout,16)
     int* acc_tap;
