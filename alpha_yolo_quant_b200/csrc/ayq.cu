@@ -908,8 +908,16 @@ static int run_pass(ayq_engine* e, const float* img, const uint8_t* img_u8, int 
     return 0;
 }
 
+static int forward_device(ayq_handle e, const float* img, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream);
 extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream) {
     if (!e || !img || !dets || !counts || n < 0) return fail(-22, "ayq_forward: bad arguments");
+    return forward_device(e, img, nullptr, n, dbox_cls, dets, counts, stream);
+}
+extern "C" int ayq_forward_u8(ayq_handle e, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream) {
+    if (!e || !img_u8 || !dets || !counts || n < 0) return fail(-22, "ayq_forward_u8: bad arguments");
+    return forward_device(e, nullptr, img_u8, n, dbox_cls, dets, counts, stream);
+}
+static int forward_device(ayq_handle e, const float* img, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream) {
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -921,7 +929,8 @@ extern "C" int ayq_forward(ayq_handle e, const float* img, int n, float* dbox_cl
     const size_t img_elems = (size_t)3 * e->hdr.img_h * e->hdr.img_w;
     for (int i0 = 0; i0 < n; i0 += mb) {
         const int m = (n - i0) < mb ? (n - i0) : mb;
-        rc = run_pass(e, img + (size_t)i0 * img_elems, nullptr, m, dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
+        rc = run_pass(e, img ? img + (size_t)i0 * img_elems : nullptr, img_u8 ? img_u8 + (size_t)i0 * img_elems : nullptr, m,
+                      dbox_cls ? dbox_cls + (size_t)i0 * 84 * e->hdr.n_anchors : nullptr,
                       dets + (size_t)i0 * AYQ_MAX_DET * AYQ_DET_STRIDE, counts + i0, st);
         if (rc) { mark_busy(e, st); return rc; }
     }

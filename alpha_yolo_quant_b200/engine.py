@@ -28,6 +28,7 @@ SIGNATURES = {
     'ayq_set_max_batch': (_int, [_vp, _int]),
     'ayq_workspace_bytes': (_sz, [_vp]),
     'ayq_forward': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    'ayq_forward_u8': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp]),
     'ayq_forward_host': (_int, [_vp, _vp, _int, _vp, _vp]),
     'ayq_forward_host_u8': (_int, [_vp, _vp, _int, _vp, _vp]),
     'ayq_forward_host_async': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
@@ -127,24 +128,26 @@ class Engine:
 
     # -- hot path
     def forward(self, img, want_dbox_cls=False):
-        """img: CUDA float32 (n,3,640,640).  Returns (dets (n,300,6), counts (n) int32[, dbox_cls (n,84,8400)])."""
+        """img: CUDA float32 (n,3,640,640) in [0,1], or CUDA uint8 (n,3,640,640) (ToTensor then runs inside Conv_P1).
+        Returns (dets (n,300,6), counts (n) int32[, dbox_cls (n,84,8400)])."""
         _require_cuda(img, 'Engine.forward')
-        if img.dtype != torch.float32 or img.dim() != 4 or tuple(img.shape[1:]) != (3, 640, 640):
-            raise AyqError(f'Engine.forward: expected float32 (n,3,640,640), got {img.dtype} {tuple(img.shape)}')
+        if img.dtype not in (torch.float32, torch.uint8) or img.dim() != 4 or tuple(img.shape[1:]) != (3, 640, 640):
+            raise AyqError(f'Engine.forward: expected float32 or uint8 (n,3,640,640), got {img.dtype} {tuple(img.shape)}')
         img = img.contiguous()
         n = img.shape[0]
         with torch.cuda.device(self.device):
             dets = torch.empty((n, MAX_DET, DET_STRIDE), dtype=torch.float32, device=self.device)
             counts = torch.empty((n,), dtype=torch.int32, device=self.device)
             dbc = torch.empty((n, 84, ANCHORS), dtype=torch.float32, device=self.device) if want_dbox_cls else None
-            self._ck(self.lib.ayq_forward(self._h, img.data_ptr(), n, dbc.data_ptr() if dbc is not None else None,
-                                       dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
+            fn = self.lib.ayq_forward_u8 if img.dtype == torch.uint8 else self.lib.ayq_forward
+            self._ck(fn(self._h, img.data_ptr(), n, dbc.data_ptr() if dbc is not None else None,
+                        dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
         return (dets, counts, dbc) if want_dbox_cls else (dets, counts)
 
     def forward_into(self, img, dets, counts):
-        """Allocation-free variant for timing loops."""
-        self._ck(self.lib.ayq_forward(self._h, img.data_ptr(), img.shape[0], None, dets.data_ptr(), counts.data_ptr(),
-                                   _stream_ptr(self.device)))
+        """Allocation-free variant for timing loops (img: contiguous CUDA float32 or uint8 (n,3,640,640))."""
+        fn = self.lib.ayq_forward_u8 if img.dtype == torch.uint8 else self.lib.ayq_forward
+        self._ck(fn(self._h, img.data_ptr(), img.shape[0], None, dets.data_ptr(), counts.data_ptr(), _stream_ptr(self.device)))
 
     def forward_host(self, img_host, dets_host=None, counts_host=None):
         """img_host: CPU float32 or uint8 tensor (n,3,640,640) (pinned for full speed).  Synchronous."""

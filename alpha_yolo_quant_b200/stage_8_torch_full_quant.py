@@ -295,7 +295,9 @@ class Yolov8(nn.Module):
         return self._ensure_engine()
 
     def forward_batch(self, x):
-        """x (N,3,640,640) fp32 in [0,1] -> list of (boxes, classes) | (None, None); element i == model(x[i:i+1])."""
+        """x (N,3,640,640) fp32 in [0,1] -> list of (boxes, classes) | (None, None); element i == model(x[i:i+1]).
+        uint8 images (the loader's format before ToTensor, :985-990 of stage_8_torch.py) are accepted too: u8 / 255 then
+        happens on the GPU, with the same results as on (x / 255).float()."""
         e = self._ensure_engine()
         if not x.is_cuda:
             x = x.to(e.device)                 # the reference does x.to(device) inside forward (:710)

@@ -253,6 +253,25 @@ def main():
     ms_max = float(t.item())
     value = B * world * args.steps / (ms_max / 1000.0)
     n_det = int(counts.sum().item())
+    # ---- the same loop with the images resident as uint8 (the loader's format before ToTensor: ayq_forward_u8); reported beside
+    # `value`, which stays on the reference forward()'s own input format (float32 in [0,1])
+    x_u8 = torch.from_numpy(u8).cuda()
+    for _ in range(args.warmup):
+        e.forward_into(x_u8, dets, counts)
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(args.steps):
+        e.forward_into(x_u8, dets, counts)
+    ev3.record(stream)
+    barrier()
+    t8 = torch.tensor([ev2.elapsed_time(ev3)], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(t8, op=dist.ReduceOp.MAX)
+    value_u8 = {'value': B * world * args.steps / (float(t8.item()) / 1000.0), 'unit': 'images/s', 'ms_per_step': float(t8.item()) / args.steps,
+                'input': 'uint8 (B,3,640,640) resident in HBM -> ayq_forward_u8 (ToTensor + input quantiser inside Conv_P1); same detections',
+                'same_detections': int(counts.sum().item()) == n_det}
+    del x_u8
     # ---- end to end through the host-buffer C-ABI call
     e2e = None
     e2e_f32 = None
@@ -432,7 +451,7 @@ def main():
                        'global_batch': B * world, 'images_per_pass': min(B, args.max_batch), 'conv_kernel': args.conv,
                        'l2': f'inputs larger than L2 ({B * 4915200 / 1e6:.0f} MB fp32 images per step, activations {e.workspace_bytes / 1e6:.0f} MB workspace)',
                        'detections_per_step': n_det},
-            'e2e': e2e, 'e2e_f32': e2e_f32, 'gpu_launches': int(e.launches_per_pass * passes * args.steps),
+            'value_u8_resident': value_u8, 'e2e': e2e, 'e2e_f32': e2e_f32, 'gpu_launches': int(e.launches_per_pass * passes * args.steps),
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'multi_gpu_parity': parity, 'sustained': sustained,
             'whole_net': {'hbm_frac': value / world * BYTES_IMG / 1e9 / peaks['hbm'], 'int8_tops': value / world * OPS_IMG / 1e12,
                           'tensor_frac': value / world * OPS_IMG / 1e12 / peaks['int8'], 'peaks': peaks['src'], 'int8_peak_source': peaks['int8_src']},

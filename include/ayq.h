@@ -56,6 +56,10 @@ size_t ayq_workspace_bytes(ayq_handle h);
  *   dets      device, float32 (n,300,6): rows [x1,y1,x2,y2,conf,class], first counts[i] valid
  *   counts    device, int32 (n): 0 <=> the reference returns (None, None)                        */
 int ayq_forward(ayq_handle h, const float* img, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream);
+/* The same with the images as DEVICE uint8 (n,3,640,640) CHW, the loader's format before ToTensor (stage_8_torch.py:985-990; what
+ * a GPU JPEG decoder delivers): u8 / 255 and the per-image input quantiser (utils/quant_matrix_torch.py:57-70) run inside
+ * Conv_P1.  Bit-identical to ayq_forward on (u8 / 255).to(float32); a quarter of the input bytes. */
+int ayq_forward_u8(ayq_handle h, const uint8_t* img_u8, int n, float* dbox_cls, float* dets, int32_t* counts, void* stream);
 
 /* The same call with HOST buffers (validation-driver loop, stage_8_torch.py:1004-1013): H2D of the
  * images and D2H of the detections happen inside (pipelined against compute when the host buffers are

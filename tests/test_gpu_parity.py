@@ -177,6 +177,29 @@ def test_host_entry_points(golden_dir):
     e.close()
 
 
+def test_device_uint8_entry(golden_dir):
+    """ayq_forward_u8 (device uint8 images, ToTensor inside Conv_P1) == ayq_forward on (u8 / 255).float(): detections and the
+    first activation map bit for bit, over several passes (max_batch 2) and for a single image."""
+    p, e = _setup(golden_dir, 8, taps=False, max_batch=2)
+    seeds = [0, 1, 2, 5, 6]
+    u8 = torch.from_numpy(np.stack([synth.synth_image_u8(s) for s in seeds])).cuda()
+    xs = _images(seeds).cuda()
+    dets, counts = e.forward(xs)
+    du, cu, dbc_u = e.forward(u8, want_dbox_cls=True)
+    _, _, dbc_f = e.forward(xs, want_dbox_cls=True)
+    torch.cuda.synchronize()
+    assert torch.equal(cu, counts) and torch.equal(dbc_u, dbc_f)
+    for i in range(len(seeds)):
+        k = int(counts[i])
+        assert torch.equal(du[i, :k], dets[i, :k])
+    d1, c1 = e.forward(u8[[3]].contiguous())
+    assert int(c1[0]) == int(counts[3]) and torch.equal(d1[0, :int(c1[0])], dets[3, :int(c1[0])])
+    from alpha_yolo_quant_b200 import engine
+    with pytest.raises(engine.AyqError):
+        e.forward(u8.to(torch.int16))
+    e.close()
+
+
 def test_entries_on_different_streams_are_ordered_by_the_engine(golden_dir):
     """Two ayq_forward calls on two different streams share the engine's workspace: the engine serialises them (include/ayq.h,
     stream semantics), so both results must be right without any caller-side synchronisation between the calls."""
