@@ -45,6 +45,8 @@ struct ayq_engine {
     std::vector<OpDesc> ops;
     std::vector<unsigned char> host_data;
     unsigned char* d_data = nullptr;       // data section on the device
+    std::vector<signed char> conv_nq1;     // per conv op: launch-plan variant picked by the load-time tuner (tune_variant(); 0 = default, -1 = not tuned yet)
+    bool autotune = true;                  // AYQ_AUTOTUNE=0 switches the load-time tuner off
     float* d_lutrep = nullptr;             // replicated sigmoid tables (one [257][32] + one [257][8] block per distinct table of the plan)
     std::vector<const float*> op_lutrep;   // per op: its [257][32] block (convs with the SiLU epilogue) / [257][8] block (Conv_P1), else nullptr
     int max_batch = 256;
@@ -135,6 +137,20 @@ static void free_workspace(ayq_engine* e) {
 static int ensure_workspace_impl(ayq_engine* e, int n);
 static void build_conv_args(ayq_engine* e, int opi, int n, ConvArgs& a);
 static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a);
+static int tune_conv(ayq_engine* e, int opi, int n, const ConvArgs& a);
+// launch-plan variants the load-time tuner chooses from (all compute the same bits; they differ in how the CTA's shared memory,
+// TMEM and control warps are split)
+static const int AYQ_TUNE_VARIANTS = 3;
+static const char* const AYQ_TUNE_NAMES[AYQ_TUNE_VARIANTS] = {"default", "one chain per pipeline", "one accumulator per epilogue group"};
+// (measured and dropped from the list: weights resident up to 160 KB / streamed above 32 KB -- never faster, up to 50 % slower;
+//  control warps on the highest warp ids / no halo boxes for 16-channel inputs -- within the timing noise)
+static void tune_variant(TmaState& s, int v) {
+    switch (v) {
+    case 1: s.force_nq1 = 1; break;
+    case 2: s.nbuf_mul = 1; break;
+    default: break;
+    }
+}
 static int ensure_workspace(ayq_engine* e, int n) {
     if (n <= e->cap) return 0;
     const int rc = ensure_workspace_impl(e, n);
@@ -219,9 +235,12 @@ static int ensure_workspace_impl(ayq_engine* e, int n) {
             if (e->ops[i].f[0] != OP_CONV) continue;
             ConvArgs a;
             build_conv_args(e, (int)i, cap, a);
+            if (e->conv_nq1.size() != e->ops.size()) e->conv_nq1.assign(e->ops.size(), -1);
             if (!prepare_tma_conv(e, (int)i, cap, a))
                 return fail(-38, "conv op %zu (%s): shape not covered by the TMA-fed tcgen05 kernel (cout %d, %dx%d, stride %d, %d K chunks)", i,
                             (const char*)(e->host_data.data() + e->ops[i].f[CF_NAME_OFF]), a.cout, a.Hout, a.Wout, a.stride, a.nkc);
+            int rc = tune_conv(e, (int)i, cap, a);
+            if (rc) return rc;
         }
     }
     return 0;
@@ -361,6 +380,7 @@ extern "C" int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_
 #endif
     e->p1_dp4a = getenv("AYQ_P1_DP4A") != nullptr;
     e->guard = getenv("AYQ_WS_GUARD") != nullptr;
+    e->autotune = !(getenv("AYQ_AUTOTUNE") && atoi(getenv("AYQ_AUTOTUNE")) == 0);
     e->p1_fuse = getenv("AYQ_P1_FUSE") != nullptr;           // off: measured slower than the two kernels (843 vs 184 + 439 us per 256 images)
     if (const char* ev = getenv("AYQ_P1_CHUNK")) e->p1_chunk = atoi(ev);
     if (const char* ev = getenv("AYQ_HOST_PASS")) e->host_pass = atoi(ev);
@@ -529,6 +549,13 @@ extern "C" int ayq_get_conv_impls(ayq_handle e, int32_t* impl, int cap) {
         impl[i] = e->ops[i].f[0] == OP_CONV ? (i < (int)e->conv_impl_used.size() ? e->conv_impl_used[i] : -1) : -2;
     return n < cap ? n : cap;
 }
+extern "C" int ayq_get_conv_variants(ayq_handle e, int32_t* variant, int cap) {
+    if (!e || !variant) return fail(-22, "ayq_get_conv_variants: bad arguments");
+    const int n = (int)e->ops.size();
+    for (int i = 0; i < n && i < cap; ++i)
+        variant[i] = e->ops[i].f[0] == OP_CONV ? (i < (int)e->conv_nq1.size() ? (int)e->conv_nq1[i] : -1) : -2;
+    return n < cap ? n : cap;
+}
 // Own bounds check (compute-sanitizer is closed on the GPU pool this was developed on): with AYQ_WS_GUARD=1 every activation buffer
 // of the workspace is followed by a 4 KB canary zone; returns the number of canary bytes any kernel has overwritten (0 = clean).
 extern "C" int ayq_check_guards(ayq_handle e) {
@@ -587,7 +614,9 @@ static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {
     const float* h_tab = (const float*)(e->host_data.data() + f[CF_TAB_OFF]);
     const int* h_bias = (const int*)(e->host_data.data() + f[CF_BIAS_OFF]);
     if (L.n != n) {
-        tma_prepare(e->tma, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
+        TmaState ts = e->tma;
+        if ((size_t)opi < e->conv_nq1.size() && e->conv_nq1[opi] > 0) tune_variant(ts, e->conv_nq1[opi]);
+        tma_prepare(ts, L, a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), h_tab, h_bias,
                     (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
         if (getenv("AYQ_PLAN_DUMP"))
             fprintf(stderr, "plan %-20s n=%d ok=%d cout=%3d %3dx%-3d s%d nkc=%3d | %s fast=%d gen=%d resB=%d NS=%2d slot=%5dB nbuf=%d tiles=%d smem=%zuK grid=%u\n",
@@ -595,6 +624,59 @@ static int prepare_tma_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {
                     L.pl.halo ? "halo " : "boxes", L.fast, L.gen_outs, L.tp.resident_b, L.tp.NS, L.pl.a_slot_bytes, L.tp.nbuf, L.tp.ntiles, L.smem / 1024, L.grid);
     }
     return L.ok;
+}
+// Load-time tuner (runs when the workspace is built, never inside a pass).  The default launch plan of a layer (two producer ->
+// issuer chains per pipeline, two accumulators per epilogue group, weights resident up to 96 KB, ...) is the best on average;
+// single layers measure a few us faster with another split of the CTA's resources (e.g. ONE chain with the whole ring on the
+// 20x20 layers with streamed weights and on some halo layers: fewer, deeper rings balance the few tiles a CTA gets).  Every
+// variant computes the same bits; each sufficiently large layer is timed with all of them on whatever the workspace holds (best
+// of three pairs of launches, 2 % hysteresis in favour of the default) and the choice is kept for every pass size of the engine.
+static int tune_conv(ayq_engine* e, int opi, int n, const ConvArgs& a) {
+    TmaLaunch& L = e->tma_cache[opi];
+    if (e->conv_nq1[opi] != -1) return 0;
+    e->conv_nq1[opi] = 0;
+    if (!e->autotune || e->role_prof) return 0;
+    if (!L.ok || L.tp.ntiles < 2 * (int)L.grid) return 0;         // too small to matter
+    const int32_t* f = e->ops[opi].f;
+    std::vector<TmaLaunch> cand(AYQ_TUNE_VARIANTS);
+    std::vector<int> live;
+    cand[0] = L; live.push_back(0);
+    for (int v = 1; v < AYQ_TUNE_VARIANTS; ++v) {
+        TmaState ts = e->tma;
+        tune_variant(ts, v);
+        tma_prepare(ts, cand[v], a, e->h_kc[opi].data(), e->tma_segs[opi].data(), (int)e->tma_segs[opi].size(), (const float*)(e->host_data.data() + f[CF_TAB_OFF]),
+                    (const int*)(e->host_data.data() + f[CF_BIAS_OFF]), (const float*)(e->host_data.data() + f[CF_LUT_OFF]), (const int8_t*)(e->host_data.data() + f[CF_W_OFF]));
+        if (!cand[v].ok) continue;
+        const tc::TcParams &x = cand[v].tp, &y = L.tp;            // identical to the default plan: nothing to measure
+        if (x.NS == y.NS && x.KS == y.KS && x.nbuf == y.nbuf && x.nq == y.nq && x.resident_b == y.resident_b && x.role_hi == y.role_hi &&
+            cand[v].pl.halo == L.pl.halo && cand[v].smem == L.smem) continue;
+        live.push_back(v);
+    }
+    if (live.size() < 2) return 0;
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    std::vector<float> best(AYQ_TUNE_VARIANTS, 1e30f);
+    for (int rep = 0; rep < 4; ++rep)                             // rep 0: warm-up
+        for (int v : live) {
+            CK(cudaEventRecord(ev0, 0));
+            for (int k = 0; k < 2; ++k)
+                if (tma_launch(cand[v], a, 0) != 0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(-5, "tuner: conv launch failed for op %d (variant %d)", opi, v); }
+            CK(cudaEventRecord(ev1, 0));
+            CK(cudaEventSynchronize(ev1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev0, ev1));
+            if (rep > 0 && ms < best[v]) best[v] = ms;
+        }
+    CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
+    int pick = 0;
+    for (int v : live) if (v && best[v] < 0.98f * best[0] && best[v] < best[pick]) pick = v;
+    if (pick) { e->conv_nq1[opi] = (signed char)pick; L = cand[pick]; }
+    if (getenv("AYQ_PLAN_DUMP")) {
+        fprintf(stderr, "tune %-20s", (const char*)(e->host_data.data() + f[CF_NAME_OFF]));
+        for (int v : live) fprintf(stderr, " v%d %.1f", v, best[v] * 500.f);
+        fprintf(stderr, " us -> %s\n", AYQ_TUNE_NAMES[pick]);
+    }
+    return 0;
 }
 static int launch_conv(ayq_engine* e, int opi, int n, cudaStream_t st) {
     const int32_t* f = e->ops[opi].f;

@@ -419,7 +419,8 @@ struct TmaLaunch {            // everything one launch needs, cached per (op, im
     int gen_outs = 0;         // MAGIC with a general output list
 };
 
-struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 1; int budget_kb = 208; int resident_kb = 96; int role_hi = 0; int nbuf_mul = 2; };
+struct TmaState { PFN_tmapEncodeTiled encode = nullptr; int num_sms = 148; int ready = 0; int halo_min_np = 1; int budget_kb = 208; int resident_kb = 96; int role_hi = 0; int nbuf_mul = 2;
+                  int force_nq1 = 0; };   // force_nq1: one producer -> issuer chain per pipeline (AYQ_ONE_ISSUER=1, or the per-layer choice of the load-time tuner)
 
 typedef void (*TmaKernel)(const ConvArgs, const tc::TcParams, const tc::EpiTab, const tc::TmaPlan, const tc::TmaMaps);
 template <int FAST>
@@ -522,6 +523,7 @@ static inline void tma_init(TmaState& s) {
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (const char* ev = getenv("AYQ_HALO_MIN_NP")) s.halo_min_np = atoi(ev);
     if (const char* ev = getenv("AYQ_ROLE_HI")) s.role_hi = atoi(ev);
+    if (const char* ev = getenv("AYQ_ONE_ISSUER")) s.force_nq1 = atoi(ev) != 0;
     if (const char* ev = getenv("AYQ_NBUF_MUL")) s.nbuf_mul = atoi(ev);   // 1: one accumulator buffer per epilogue group (round-1 behaviour)
     if (const char* ev = getenv("AYQ_SMEM_KB")) s.budget_kb = atoi(ev);          // experiments: smaller CTAs let consecutive kernels co-reside
     if (const char* ev = getenv("AYQ_RESIDENT_KB")) s.resident_kb = atoi(ev);   // 16-channel inputs (np = 1) pair taps 16 B apart: slower than plain boxes
@@ -598,7 +600,7 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     if (nbuf > tc::TMA_NB) nbuf = tc::TMA_NB;
     // two producer -> ring -> issuer chains per pipeline when its accumulators split evenly between them (private even / odd
     // buffers); an odd count (cout 80: three) keeps them all with a single chain -- measured faster than two chains with one each
-    tp.nq = nbuf >= 2 && (nbuf & 1) == 0 && !getenv("AYQ_ONE_ISSUER") ? 2 : 1;
+    tp.nq = nbuf >= 2 && (nbuf & 1) == 0 && !s.force_nq1 ? 2 : 1;
     tp.nbuf = nbuf;
     while (cols < 2 * nbuf * N) cols <<= 1;                       // two pipelines x nbuf accumulators
     tp.tmem_cols = cols;

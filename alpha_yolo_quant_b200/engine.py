@@ -34,6 +34,7 @@ SIGNATURES = {
     'ayq_forward_host_async': (_int, [_vp, _vp, _int, _int, _vp, _vp]),
     'ayq_wait': (_int, [_vp]),
     'ayq_get_conv_impls': (_int, [_vp, _vp, _int]),
+    'ayq_get_conv_variants': (_int, [_vp, _vp, _int]),
     'ayq_check_guards': (_int, [_vp]),
     'ayq_export_buffer': (_int, [_vp, _int, _int, _vp, _vp]),
     'ayq_buffer_shape': (_int, [_vp, _int, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_int)]),
@@ -193,6 +194,14 @@ class Engine:
         n = self.plan.n_ops
         out = np.zeros(n, np.int32)
         self._ck(self.lib.ayq_get_conv_impls(self._h, out.ctypes.data, n))
+        return out
+
+    def conv_variants(self):
+        """Per plan op: the launch-plan variant the load-time tuner picked (0 default, 1 one chain per pipeline, 2 one accumulator
+        per epilogue group; -1 not built yet, -2 not a conv).  All variants are bit-identical."""
+        n = self.plan.n_ops
+        out = np.zeros(n, np.int32)
+        self._ck(self.lib.ayq_get_conv_variants(self._h, out.ctypes.data, n))
         return out
 
     def nms(self, dbox_cls):

@@ -200,6 +200,39 @@ def test_device_uint8_entry(golden_dir):
     e.close()
 
 
+def test_launch_plan_variants_are_bit_identical(golden_dir, monkeypatch):
+    """The load-time tuner picks a launch-plan variant per layer (include/ayq.h: ayq_get_conv_variants).  Every variant must compute
+    the same bits: tuned engine == untuned engine == engines with variant 1 / variant 2 forced on every layer (64 images: enough
+    tiles per CTA for the tuner to engage), detections and the (n,84,8400) head tensor."""
+    from alpha_yolo_quant_b200 import engine
+    xs = _images(list(range(8))).repeat(8, 1, 1, 1).cuda()
+    ref = None
+    for env in ({}, {'AYQ_AUTOTUNE': '0'}, {'AYQ_AUTOTUNE': '0', 'AYQ_ONE_ISSUER': '1'}, {'AYQ_AUTOTUNE': '0', 'AYQ_NBUF_MUL': '1'}):
+        for k in ('AYQ_AUTOTUNE', 'AYQ_ONE_ISSUER', 'AYQ_NBUF_MUL'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        p, e = _setup(golden_dir, 8, taps=False, max_batch=64)
+        d, c, dbc = e.forward(xs, want_dbox_cls=True)
+        torch.cuda.synchronize()
+        v = e.conv_variants()
+        convs = v[v > -2]
+        if env:
+            assert (convs == 0).all(), (env, convs)               # tuner off: default plan everywhere (forced variants come from the environment)
+        else:
+            assert (convs >= 0).all() and (convs <= 2).all()
+            print('tuner picks:', {int(k): int((convs == k).sum()) for k in (0, 1, 2)})
+        assert (e.conv_impls()[v > -2] == 2).all()
+        if ref is None:
+            ref = (d.clone(), c.clone(), dbc.clone())
+        else:
+            assert torch.equal(c, ref[1]) and torch.equal(dbc, ref[2]), env
+            for i in range(xs.shape[0]):
+                k = int(c[i])
+                assert torch.equal(d[i, :k], ref[0][i, :k]), (env, i)
+        e.close()
+
+
 def test_entries_on_different_streams_are_ordered_by_the_engine(golden_dir):
     """Two ayq_forward calls on two different streams share the engine's workspace: the engine serialises them (include/ayq.h,
     stream semantics), so both results must be right without any caller-side synchronisation between the calls."""
