@@ -96,8 +96,8 @@ int ayq_set_conv_impl(ayq_handle h, int impl);
 /* per conv op of the last pass, which implementation ran it (2 / 1 / 0 as above, -1 not run yet); returns the number of ops
  * written (ops that are not convolutions get -2).  Parity tests assert that every conv ran on the TMA kernel. */
 int ayq_get_conv_impls(ayq_handle h, int32_t* impl, int cap);
-/* Launch-plan variant of every conv op, chosen by the load-time tuner when the workspace is built (AYQ_AUTOTUNE=0 in the
- * environment of ayq_create switches it off): 0 = default (two producer -> issuer chains per pipeline, two accumulators per
+/* Launch-plan variant of every conv op.  With AYQ_AUTOTUNE=1 in the environment of ayq_create a load-time tuner times the
+ * variants of every sufficiently large layer when the workspace is built and keeps the fastest (default: off, variant 0 everywhere): 0 = default (two producer -> issuer chains per pipeline, two accumulators per
  * epilogue group), 1 = one chain per pipeline, 2 = one accumulator per epilogue group; -1 = workspace not built yet, -2 = not a
  * convolution.  All variants compute the same bits; layers with fewer than two tiles per CTA are not tuned. */
 int ayq_get_conv_variants(ayq_handle h, int32_t* variant, int cap);
