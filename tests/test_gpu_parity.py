@@ -177,13 +177,17 @@ def test_host_entry_points(golden_dir):
     e.close()
 
 
-def test_device_uint8_entry(golden_dir):
+@pytest.mark.parametrize('k', [8, 6, 4])
+def test_device_uint8_entry(golden_dir, k):
     """ayq_forward_u8 (device uint8 images, ToTensor inside Conv_P1) == ayq_forward on (u8 / 255).float(): detections and the
-    first activation map bit for bit, over several passes (max_batch 2) and for a single image."""
-    p, e = _setup(golden_dir, 8, taps=False, max_batch=2)
+    (n,84,8400) head tensor bit for bit, over several passes (max_batch 2) and for a single image; K = 6 / 4 take the clamping
+    Conv_P1 variant; an all-black image (max|x| = 0: the input quantiser's zero branch) rides along."""
+    p, e = _setup(golden_dir, k, taps=False, max_batch=2)
     seeds = [0, 1, 2, 5, 6]
-    u8 = torch.from_numpy(np.stack([synth.synth_image_u8(s) for s in seeds])).cuda()
-    xs = _images(seeds).cuda()
+    u8_np = np.stack([synth.synth_image_u8(s) for s in seeds])
+    u8_np[2] = 0
+    u8 = torch.from_numpy(u8_np).cuda()
+    xs = torch.from_numpy(synth.to_input_array(list(u8_np))).cuda()
     dets, counts = e.forward(xs)
     du, cu, dbc_u = e.forward(u8, want_dbox_cls=True)
     _, _, dbc_f = e.forward(xs, want_dbox_cls=True)
