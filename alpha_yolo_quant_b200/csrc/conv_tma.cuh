@@ -600,7 +600,10 @@ static inline int tma_prepare(TmaState& s, TmaLaunch& L, const ConvArgs& a, cons
     if (nbuf > tc::TMA_NB) nbuf = tc::TMA_NB;
     // two producer -> ring -> issuer chains per pipeline when its accumulators split evenly between them (private even / odd
     // buffers); an odd count (cout 80: three) keeps them all with a single chain -- measured faster than two chains with one each
-    tp.nq = nbuf >= 2 && (nbuf & 1) == 0 && !s.force_nq1 ? 2 : 1;
+    // ... and layers whose weights are streamed through the ring (K x cout x 16 B > 96 KB: the 1152- / 2304-K convs at 20x20) keep one
+    // chain per pipeline as well: half as many, twice as deep rings (measured 2-5 us per layer, consistently: DESIGN.md, tuner)
+    const bool streamed_b = (size_t)tp.nkc_pad * N * 16 > (size_t)s.resident_kb * 1024;
+    tp.nq = nbuf >= 2 && (nbuf & 1) == 0 && !s.force_nq1 && !streamed_b ? 2 : 1;
     tp.nbuf = nbuf;
     while (cols < 2 * nbuf * N) cols <<= 1;                       // two pipelines x nbuf accumulators
     tp.tmem_cols = cols;
