@@ -49,7 +49,7 @@ struct ayq_engine {
     bool autotune = false;                 // AYQ_AUTOTUNE=1 switches the load-time tuner on
     float* d_lutrep = nullptr;             // replicated sigmoid tables (one [257][32] + one [257][8] block per distinct table of the plan)
     std::vector<const float*> op_lutrep;   // per op: its [257][32] block (convs with the SiLU epilogue) / [257][8] block (Conv_P1), else nullptr
-    int max_batch = 256;
+    int max_batch = 512;
     int cap = 0;                           // images the workspace is sized for
     unsigned char* ws = nullptr;
     size_t ws_bytes = 0;

@@ -96,7 +96,7 @@ class DataParallelYolo:
     fails loudly without one.
     """
 
-    def __init__(self, plan, devices=None, max_batch=256, group=None, engine_factory=None):
+    def __init__(self, plan, devices=None, max_batch=512, group=None, engine_factory=None):
         if engine_factory is None:
             from . import engine as _eng
             engine_factory = _eng.Engine

@@ -101,7 +101,7 @@ def _require_cuda(t, name):
 class Engine:
     """One handle per GPU (not thread-safe), created from a compiled plan (plan.compile_plan)."""
 
-    def __init__(self, plan, device=0, max_batch=256, lib_path=None):
+    def __init__(self, plan, device=0, max_batch=512, lib_path=None):
         self.lib = load_library(lib_path)
         if not torch.cuda.is_available():
             raise AyqError('Engine: no CUDA device available; the integer YOLOv8n path has no CPU fallback')

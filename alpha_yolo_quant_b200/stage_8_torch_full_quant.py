@@ -242,7 +242,7 @@ class Yolov8(nn.Module):
     """Quantised YOLOv8n with the reference's state_dict layout (Appendix D: 63 x {weight,bias} + dfl.weight).
     The tensors are only the container load_state_dict() fills; forward() runs the compiled CUDA plan."""
 
-    def __init__(self, max_batch=256, taps=False):
+    def __init__(self, max_batch=512, taps=False):
         super().__init__()
         for prefix, cout, cin, k in _conv_shapes():
             seq, idx = prefix.split('.')

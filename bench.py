@@ -183,7 +183,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
-    ap.add_argument('--max-batch', type=int, default=256, help='images per internal pass of the engine')
+    ap.add_argument('--max-batch', type=int, default=512, help='images per internal pass of the engine')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--conv', default='tma', choices=['tma'], help='the product library has one convolution kernel family')
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU-baseline sample (images)')

